@@ -1,0 +1,246 @@
+/*
+ * runtime.cu -- device selection, the compute stream, device memory, scalar slots, CUDA-graph
+ * record/replay and the host<->device copies of the public C-ABI (include/hpgmg_b200.h).
+ *
+ * The reference has no counterpart (it is a host program: MALLOC is posix_memalign,
+ * level.c:24-40; timers are omp_get_wtime, timers/omp.c).  One process drives one GPU.
+ */
+#include <string.h>
+#include <time.h>
+#include <vector>
+
+#include "common.cuh"
+
+cudaStream_t g_stream = 0;
+unsigned long long g_launches = 0;
+int g_capturing = 0;
+
+static int g_initialised = 0;
+static int g_device = -1;
+static int g_verbose = 1;
+static int g_smoother = HPGMG_SMOOTHER_GSRB;
+static int g_use_graphs = 1;
+static int g_profile = 0;
+static double *g_scalars = NULL;            /* device, HPGMG_NUM_SCALARS doubles */
+static double *g_scalars_host = NULL;       /* pinned mirror                      */
+static cudaEvent_t g_ev0, g_ev1;
+static double g_last_device_seconds = 0.0;
+
+void hpgmg_cuda_check(cudaError_t e, const char *what, const char *file, int line)
+{
+  if (e == cudaSuccess) return;
+  fprintf(stderr, "hpgmg_b200: CUDA error %s (%s) at %s:%d in `%s`\n", cudaGetErrorName(e), cudaGetErrorString(e), file, line, what);
+  fflush(stderr);
+  abort();
+}
+
+static void require_init(const char *who)
+{
+  if (g_initialised) return;
+  /* lazy init on device 0 (or HPGMG_B200_DEVICE / LOCAL_RANK) so that a reference-style main()
+   * that knows nothing about GPUs still works; failure is fatal -- there is no CPU path */
+  int dev = 0;
+  const char *e = getenv("HPGMG_B200_DEVICE");
+  if (!e) e = getenv("LOCAL_RANK");
+  if (e) dev = atoi(e);
+  if (hpgmg_b200_init(dev) != 0) {
+    fprintf(stderr, "hpgmg_b200: %s needs a CUDA device (sm_100a) and none could be initialised; there is no CPU fallback\n", who);
+    exit(1);
+  }
+}
+
+extern "C" int hpgmg_b200_init(int device_ordinal)
+{
+  if (g_initialised) return 0;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    fprintf(stderr, "hpgmg_b200_init: no CUDA device (%s)\n", e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+    return 1;
+  }
+  if (device_ordinal < 0 || device_ordinal >= count) device_ordinal = device_ordinal % count;
+  e = cudaSetDevice(device_ordinal);
+  if (e != cudaSuccess) { fprintf(stderr, "hpgmg_b200_init: cudaSetDevice(%d): %s\n", device_ordinal, cudaGetErrorString(e)); return 2; }
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, device_ordinal));
+  if (prop.major < 10) {
+    fprintf(stderr, "hpgmg_b200_init: device %d is sm_%d%d; this library carries sm_100a code only\n", device_ordinal, prop.major, prop.minor);
+    return 3;
+  }
+  g_device = device_ordinal;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaMalloc(&g_scalars, HPGMG_NUM_SCALARS * sizeof(double)));
+  CUDA_CHECK(cudaMemset(g_scalars, 0, HPGMG_NUM_SCALARS * sizeof(double)));
+  CUDA_CHECK(cudaMallocHost(&g_scalars_host, HPGMG_NUM_SCALARS * sizeof(double)));
+  CUDA_CHECK(cudaEventCreate(&g_ev0));
+  CUDA_CHECK(cudaEventCreate(&g_ev1));
+  g_initialised = 1;
+  return 0;
+}
+
+extern "C" void hpgmg_b200_finalize(void)
+{
+  if (!g_initialised) return;
+  cudaStreamSynchronize(g_stream);
+  hpgmg_graph_drop_all(NULL);
+  cudaFree(g_scalars);  cudaFreeHost(g_scalars_host);
+  cudaEventDestroy(g_ev0);  cudaEventDestroy(g_ev1);
+  cudaStreamDestroy(g_stream);
+  g_stream = 0;  g_initialised = 0;
+}
+
+extern "C" void hpgmg_b200_sync(void) { require_init("sync"); CUDA_CHECK(cudaStreamSynchronize(g_stream)); }
+extern "C" const char *hpgmg_b200_backend(void) { return "cuda-sm_100a"; }
+extern "C" void *hpgmg_b200_stream(void) { require_init("stream"); return (void *)g_stream; }
+extern "C" int hpgmg_b200_device(void) { return g_device; }
+
+extern "C" void hpgmg_b200_set_smoother(int which) { g_smoother = which; }
+extern "C" int  hpgmg_b200_get_smoother(void) { return g_smoother; }
+extern "C" void hpgmg_b200_set_verbose(int on) { g_verbose = on; }
+extern "C" void hpgmg_b200_use_graphs(int on) { g_use_graphs = on; }
+extern "C" void hpgmg_b200_profile_operators(int on) { g_profile = on; }
+
+extern "C" int hpgmg_rt_verbose(void) { return g_verbose; }
+extern "C" int hpgmg_rt_smoother(void) { return g_smoother; }
+extern "C" int hpgmg_rt_use_graphs(void) { return g_use_graphs; }
+extern "C" int hpgmg_rt_profile(void) { return g_profile; }
+extern "C" double hpgmg_rt_wtime(void)
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+extern "C" void *hpgmg_rt_alloc_zero(size_t bytes)
+{
+  require_init("alloc");
+  if (bytes == 0) bytes = 8;
+  void *p = NULL;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "hpgmg_b200: cudaMalloc(%zu bytes) failed: %s\n", bytes, cudaGetErrorString(e));
+    exit(0);                                           /* the reference exits on malloc failure too (level.c:339) */
+  }
+  CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, g_stream));
+  return p;
+}
+extern "C" void hpgmg_rt_free(void *p) { if (p) { CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaFree(p)); } }
+extern "C" void *MALLOC(size_t size) { return hpgmg_rt_alloc_zero(size); }
+extern "C" void  FREE(void *ptr) { hpgmg_rt_free(ptr); }
+
+extern "C" void hpgmg_rt_copy_d2d(void *dst, const void *src, size_t bytes) { CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_stream)); }
+extern "C" void hpgmg_rt_copy_h2d(void *dst, const void *src, size_t bytes) { CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream)); }
+extern "C" void hpgmg_rt_copy_d2h(void *dst, const void *src, size_t bytes) { CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream)); }
+extern "C" void hpgmg_rt_sync(void) { if (g_initialised) CUDA_CHECK(cudaStreamSynchronize(g_stream)); }
+
+extern "C" void *hpgmg_b200_host_alloc_pinned(size_t bytes)
+{
+  require_init("pinned alloc");
+  void *p = NULL;
+  CUDA_CHECK(cudaMallocHost(&p, bytes ? bytes : 8));
+  return p;
+}
+extern "C" void hpgmg_b200_host_free_pinned(void *p) { if (p) CUDA_CHECK(cudaFreeHost(p)); }
+
+extern "C" void hpgmg_download_box_vector(level_type *level, int box, int id, double *host)
+{
+  const box_type *B = &level->my_boxes[box];
+  hpgmg_rt_copy_d2h(host, B->vectors[id], (size_t)B->volume * sizeof(double));
+  hpgmg_rt_sync();
+}
+extern "C" void hpgmg_upload_box_vector(level_type *level, int box, int id, const double *host)
+{
+  const box_type *B = &level->my_boxes[box];
+  hpgmg_rt_copy_h2d(B->vectors[id], host, (size_t)B->volume * sizeof(double));
+  hpgmg_rt_sync();
+}
+
+/* ------------------------------------------------------------------------------------------ */
+extern "C" double *hpgmg_rt_scalar_slots(void) { require_init("scalars"); return g_scalars; }
+extern "C" void hpgmg_rt_read_scalars(double *host, int first, int count)
+{
+  CUDA_CHECK(cudaMemcpyAsync(g_scalars_host + first, g_scalars + first, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
+  CUDA_CHECK(cudaStreamSynchronize(g_stream));
+  memcpy(host, g_scalars_host + first, (size_t)count * sizeof(double));
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* CUDA-graph record / replay keyed by (owner, key) */
+struct GraphEntry {
+  const void *owner;
+  long long key;
+  cudaGraphExec_t exec;
+  unsigned long long kernels;
+};
+static std::vector<GraphEntry> g_graphs;
+static unsigned long long g_capture_start_launches = 0;
+
+extern "C" int hpgmg_graph_begin(const void *owner, long long key)
+{
+  for (size_t i = 0; i < g_graphs.size(); i++) {
+    if (g_graphs[i].owner == owner && g_graphs[i].key == key) {
+      CUDA_CHECK(cudaGraphLaunch(g_graphs[i].exec, g_stream));
+      g_launches += g_graphs[i].kernels;
+      return 0;
+    }
+  }
+  CUDA_CHECK(cudaStreamBeginCapture(g_stream, cudaStreamCaptureModeThreadLocal));
+  g_capturing = 1;
+  g_capture_start_launches = g_launches;
+  return 1;
+}
+
+extern "C" void hpgmg_graph_end(const void *owner, long long key)
+{
+  cudaGraph_t graph = NULL;
+  CUDA_CHECK(cudaStreamEndCapture(g_stream, &graph));
+  g_capturing = 0;
+  GraphEntry e;
+  e.owner = owner;  e.key = key;  e.kernels = g_launches - g_capture_start_launches;
+  CUDA_CHECK(cudaGraphInstantiate(&e.exec, graph, 0));
+  CUDA_CHECK(cudaGraphDestroy(graph));
+  g_graphs.push_back(e);
+  /* the capture only recorded the work: run it now */
+  CUDA_CHECK(cudaGraphLaunch(e.exec, g_stream));
+}
+
+extern "C" void hpgmg_graph_drop_all(const void *owner)
+{
+  for (size_t i = 0; i < g_graphs.size();) {
+    if (owner == NULL || g_graphs[i].owner == owner) {
+      cudaGraphExecDestroy(g_graphs[i].exec);
+      g_graphs.erase(g_graphs.begin() + i);
+    } else i++;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------ */
+extern "C" void hpgmg_rt_timer_start(void) { CUDA_CHECK(cudaEventRecord(g_ev0, g_stream)); }
+extern "C" void hpgmg_rt_timer_stop(void) { CUDA_CHECK(cudaEventRecord(g_ev1, g_stream)); }
+extern "C" double hpgmg_b200_device_seconds_last_solve(void)
+{
+  float ms = 0.f;
+  CUDA_CHECK(cudaEventSynchronize(g_ev1));
+  CUDA_CHECK(cudaEventElapsedTime(&ms, g_ev0, g_ev1));
+  g_last_device_seconds = 1e-3 * (double)ms;
+  return g_last_device_seconds;
+}
+extern "C" unsigned long long hpgmg_b200_kernel_launches(void) { return g_launches; }
+
+/* ------------------------------------------------------------------------------------------ */
+/* End-to-end solve with HOST buffers: H2D of f, zero u, FMGSolve, D2H of u (bench.py's e2e). */
+extern "C" double hpgmg_fmg_solve_host(mg_type *all_grids, int onLevel, int u_id, int F_id, double a, double b,
+                                       double rtol, const double *f_host, double *u_host)
+{
+  level_type *L = all_grids->levels[onLevel];
+  const size_t vol = (size_t)L->box_volume;
+  for (int box = 0; box < L->num_my_boxes; box++)
+    hpgmg_rt_copy_h2d(L->my_boxes[box].vectors[F_id], f_host + (size_t)box * vol, vol * sizeof(double));
+  zero_vector(L, u_id);
+  FMGSolve(all_grids, onLevel, u_id, F_id, a, b, rtol);
+  for (int box = 0; box < L->num_my_boxes; box++)
+    hpgmg_rt_copy_d2h(u_host + (size_t)box * vol, L->my_boxes[box].vectors[u_id], vol * sizeof(double));
+  hpgmg_rt_sync();
+  return hpgmg_last_norm_of_residual(all_grids);
+}

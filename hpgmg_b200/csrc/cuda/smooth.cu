@@ -1,0 +1,248 @@
+/*
+ * smooth.cu -- the operator-applying kernels: GSRB and Chebyshev smoothers, residual, apply_op and
+ * the black-box diagonal rebuild.  Entry points mirror the reference one for one:
+ *   smooth            operators/gsrb.c:24-132 (GSRB_OOP + GSRB_STRIDE2) | operators/chebyshev.c:8-100
+ *   residual          operators/residual.c:9-51
+ *   apply_op          operators/apply_op.c:9-50
+ *   rebuild_operator  operators.fv4.c:145-173, rebuild_operator_blackbox operators/rebuild.c:47-208
+ *
+ * Launch geometry: a grid of (i-tiles, j-tiles, box*k-tiles) thread blocks per level; every box of
+ * a level has the same shape so one launch covers all boxes this GPU owns.
+ */
+#include <math.h>
+#include "common.cuh"
+#include "stencil.cuh"
+
+enum { OP_APPLY = 0, OP_RESIDUAL = 1, OP_GSRB = 2, OP_CHEBY = 3, OP_REBUILD = 4 };
+
+struct StencilArgs {
+  DLevel L;
+  const int *low;          /* [nboxes][3] */
+  int x_id, rhs_id, out_id, xm1_id;
+  double a, b, h2inv;
+  double c1, c2;           /* Chebyshev */
+  int sweep;               /* GSRB sweep number s (colour) */
+};
+
+/* generic one-thread-per-cell kernel (any box size) ------------------------------------------- */
+template <int OP>
+__global__ void __launch_bounds__(256) stencil_generic_kernel(const StencilArgs A)
+{
+  const DLevel &L = A.L;
+  const int n = L.dim;
+  const int ktiles = (n + blockDim.z - 1) / blockDim.z;
+  const int box = blockIdx.z / ktiles;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = (blockIdx.z % ktiles) * blockDim.z + threadIdx.z;
+  if (i >= n || j >= n || k >= n) return;
+  const int jS = L.jStride, kS = L.kStride;
+  const int ijk = i + j * jS + k * kS;
+  const double *__restrict__ x  = L.vec(box, A.x_id) + ijk;
+  const double *__restrict__ bi = L.vec(box, VECTOR_BETA_I) + ijk;
+  const double *__restrict__ bj = L.vec(box, VECTOR_BETA_J) + ijk;
+  const double *__restrict__ bk = L.vec(box, VECTOR_BETA_K) + ijk;
+
+  if (OP == OP_GSRB) {
+    double *__restrict__ out = L.vec(box, A.out_id) + ijk;
+    const int color000 = (A.low[3 * box] ^ A.low[3 * box + 1] ^ A.low[3 * box + 2] ^ A.sweep) & 1;
+    if (((i ^ j ^ k ^ color000) & 1) == 0) {
+      const double Ax = fv4_apply_op(x, bi, bj, bk, jS, kS, A.b, A.h2inv);
+      const double dinv = L.vec(box, VECTOR_DINV)[ijk];
+      const double rhs = L.vec(box, A.rhs_id)[ijk];
+      out[0] = x[0] + dinv * (rhs - Ax);
+    } else {
+      out[0] = x[0];
+    }
+    return;
+  }
+  const double Ax = fv4_apply_op(x, bi, bj, bk, jS, kS, A.b, A.h2inv);
+  if (OP == OP_APPLY) {
+    L.vec(box, A.out_id)[ijk] = Ax;
+  } else if (OP == OP_RESIDUAL) {
+    L.vec(box, A.out_id)[ijk] = L.vec(box, A.rhs_id)[ijk] - Ax;
+  } else if (OP == OP_CHEBY) {
+    const double xn = x[0];
+    const double xm1 = L.vec(box, A.xm1_id)[ijk];
+    const double dinv = L.vec(box, VECTOR_DINV)[ijk];
+    const double rhs = L.vec(box, A.rhs_id)[ijk];
+    L.vec(box, A.out_id)[ijk] = xn + A.c1 * (xn - xm1) + A.c2 * dinv * (rhs - Ax);
+  } else if (OP == OP_REBUILD) {
+    /* rebuild.c:127-133: x is a 0/1 colouring; Aii += x*Ax, sumAbsAij += |(1-x)*Ax| */
+    double *Aii = L.vec(box, A.out_id) + ijk;
+    double *sumAbs = L.vec(box, A.rhs_id) + ijk;
+    Aii[0] += (x[0]) * Ax;
+    sumAbs[0] += fabs((1.0 - x[0]) * Ax);
+  }
+}
+
+template <int OP>
+static void launch_stencil(level_type *level, StencilArgs &A)
+{
+  const DLevel &L = dl_of(level);
+  if (L.nboxes == 0) return;
+  A.L = L;
+  A.low = level->dev->low;
+  A.h2inv = 1.0 / (level->h * level->h);
+  const int n = L.dim;
+  dim3 block(n >= 32 ? 32 : (n >= 16 ? 16 : 8), n >= 32 ? 4 : 4, n >= 32 ? 2 : 4);
+  const int ktiles = (n + block.z - 1) / block.z;
+  dim3 grid((n + block.x - 1) / block.x, (n + block.y - 1) / block.y, ktiles * L.nboxes);
+  LAUNCH(stencil_generic_kernel<OP>, grid, block, 0, A);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+static void fill_ghosts(level_type *level, int id)
+{
+  exchange_boundary(level, id, stencil_get_shape());
+  apply_BCs(level, id, stencil_get_shape());
+}
+
+extern "C" int stencil_get_radius(void) { return 2; }
+extern "C" int stencil_get_shape(void) { return STENCIL_SHAPE_NO_CORNERS; }
+
+extern "C" void apply_op(level_type *level, int Ax_id, int x_id, double a, double b)
+{
+  fill_ghosts(level, x_id);
+  StencilArgs A = {};
+  A.x_id = x_id;  A.out_id = Ax_id;  A.a = a;  A.b = b;
+  launch_stencil<OP_APPLY>(level, A);
+}
+
+extern "C" void residual(level_type *level, int res_id, int x_id, int rhs_id, double a, double b)
+{
+  fill_ghosts(level, x_id);
+  StencilArgs A = {};
+  A.x_id = x_id;  A.rhs_id = rhs_id;  A.out_id = res_id;  A.a = a;  A.b = b;
+  launch_stencil<OP_RESIDUAL>(level, A);
+}
+
+static void smooth_gsrb(level_type *level, int x_id, int rhs_id, double a, double b)
+{
+  for (int s = 0; s < 6; s++) {                      /* NUM_SMOOTHS=3 -> RBRBRB (operators.fv4.c:177-180) */
+    const int src = (s & 1) == 0 ? x_id : VECTOR_TEMP;
+    const int dst = (s & 1) == 0 ? VECTOR_TEMP : x_id;
+    fill_ghosts(level, src);
+    StencilArgs A = {};
+    A.x_id = src;  A.rhs_id = rhs_id;  A.out_id = dst;  A.a = a;  A.b = b;  A.sweep = s;
+    launch_stencil<OP_GSRB>(level, A);
+  }
+}
+
+static void smooth_chebyshev(level_type *level, int x_id, int rhs_id, double a, double b)
+{
+  enum { DEGREE = 6 };                               /* CHEBYSHEV_DEGREE (operators.fv4.c:184) */
+  if (level->dominant_eigenvalue_of_DinvA <= 0.0 && level->my_rank == 0) fprintf(stderr, "dominant_eigenvalue_of_DinvA <= 0.0 !\n");
+  /* coefficients exactly as chebyshev.c:22-40 */
+  double beta = 1.000 * level->dominant_eigenvalue_of_DinvA;
+  double alpha = 0.125000 * beta;
+  double theta = 0.5 * (beta + alpha);
+  double delta = 0.5 * (beta - alpha);
+  double sigma = theta / delta;
+  double rho_n = 1 / sigma;
+  double c1[DEGREE], c2[DEGREE];
+  c1[0] = 0.0;
+  c2[0] = 1 / theta;
+  for (int s = 1; s < DEGREE; s++) {
+    double rho_nm1 = rho_n;
+    rho_n = 1.0 / (2.0 * sigma - rho_nm1);
+    c1[s] = rho_n * rho_nm1;
+    c2[s] = rho_n * 2.0 / delta;
+  }
+  for (int s = 0; s < DEGREE; s++) {
+    const int src = (s & 1) == 0 ? x_id : VECTOR_TEMP;
+    const int dst = (s & 1) == 0 ? VECTOR_TEMP : x_id;
+    fill_ghosts(level, src);
+    StencilArgs A = {};
+    A.x_id = src;  A.xm1_id = dst;  A.rhs_id = rhs_id;  A.out_id = dst;  A.a = a;  A.b = b;
+    A.c1 = c1[s % DEGREE];  A.c2 = c2[s % DEGREE];
+    launch_stencil<OP_CHEBY>(level, A);
+  }
+}
+
+extern "C" void smooth(level_type *level, int x_id, int rhs_id, double a, double b)
+{
+  if (hpgmg_rt_smoother() == HPGMG_SMOOTHER_CHEBY) smooth_chebyshev(level, x_id, rhs_id, a, b);
+  else smooth_gsrb(level, x_id, rhs_id, a, b);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* D^-1 and the Gershgorin bound on lambda_max(D^-1 A) from the operator alone (rebuild.c:47-208) */
+__global__ void rebuild_finish_kernel(const DLevel L, const int *low, int Aii_id, int sum_id, double a, double b, double h2inv, double *eig_slot)
+{
+  const int n = L.dim;
+  const int cells = n * n * n;
+  double local = 0.0;                                  /* all Di are > 0 for this operator */
+  for (int box = blockIdx.y; box < L.nboxes; box += gridDim.y) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < cells; c += gridDim.x * blockDim.x) {
+      const int i = c % n, j = (c / n) % n, k = c / (n * n);
+      const int ijk = i + j * L.jStride + k * L.kStride;
+      double *Aii = L.vec(box, Aii_id) + ijk;
+      double *sumAbs = L.vec(box, sum_id) + ijk;
+      if (Aii[0] == 0.0) {
+        printf("Aii[%d,%d,%d]==0.0 !!!\n", i + low[3 * box], j + low[3 * box + 1], k + low[3 * box + 2]);
+        Aii[0] = a + b * h2inv;
+      }
+      const double Di = (Aii[0] + sumAbs[0]) / Aii[0];
+      if (Di > local) local = Di;
+      if (Aii[0] >= 1.5 * sumAbs[0]) sumAbs[0] = 1.0 / (Aii[0]);
+      else                           sumAbs[0] = 1.0 / (Aii[0] + 0.5 * sumAbs[0]);
+      Aii[0] = 1.0 / Aii[0];
+    }
+  }
+  atomic_max_nonneg(eig_slot, local);
+}
+
+extern "C" void rebuild_operator_blackbox(level_type *level, double a, double b, int colors_in_each_dim)
+{
+  if (level->dim.i < colors_in_each_dim) colors_in_each_dim = level->dim.i;
+  if (level->dim.j < colors_in_each_dim) colors_in_each_dim = level->dim.j;
+  if (level->dim.k < colors_in_each_dim) colors_in_each_dim = level->dim.k;
+  const int chatty = level->my_rank == 0 && hpgmg_rt_verbose();
+  if (chatty) {
+    fprintf(stdout, "  calculating D^{-1} exactly for level h=%e using %3d colors...  ", level->h, colors_in_each_dim * colors_in_each_dim * colors_in_each_dim);
+    fflush(stdout);
+  }
+  const int x_id = VECTOR_TEMP, Aii_id = VECTOR_DINV, sum_id = VECTOR_E;
+  zero_vector(level, Aii_id);
+  zero_vector(level, sum_id);
+  for (int kc = 0; kc < colors_in_each_dim; kc++)
+  for (int jc = 0; jc < colors_in_each_dim; jc++)
+  for (int ic = 0; ic < colors_in_each_dim; ic++) {
+    color_vector(level, x_id, colors_in_each_dim, ic, jc, kc);
+    fill_ghosts(level, x_id);
+    StencilArgs A = {};
+    A.x_id = x_id;  A.rhs_id = sum_id;  A.out_id = Aii_id;  A.a = a;  A.b = b;
+    launch_stencil<OP_REBUILD>(level, A);
+  }
+  double *slot = hpgmg_rt_scalar_slots() + HPGMG_SLOT_SCRATCH;
+  CUDA_CHECK(cudaMemsetAsync(slot, 0, sizeof(double), g_stream));
+  const DLevel &L = dl_of(level);
+  if (L.nboxes > 0) {
+    const int cells = L.dim * L.dim * L.dim;
+    dim3 grid((cells + 255) / 256 > 1024 ? 1024 : (cells + 255) / 256, L.nboxes);
+    LAUNCH(rebuild_finish_kernel, grid, 256, 0, L, level->dev->low, Aii_id, sum_id, a, b, 1.0 / (level->h * level->h), slot);
+  }
+  double eig = 0.0;
+  hpgmg_rt_read_scalars(&eig, HPGMG_SLOT_SCRATCH, 1);
+  if (L.nboxes == 0) eig = -1e9;
+  eig = hpgmg_comm_allreduce_max(level, eig);          /* MPI_Allreduce(MAX) over all ranks (rebuild.c:195) */
+  if (chatty) fprintf(stdout, "done\n");
+  if (chatty && hpgmg_rt_smoother() == HPGMG_SMOOTHER_CHEBY) { fprintf(stdout, "  estimating  lambda_max... <%1.15e\n", eig); fflush(stdout); }
+  level->dominant_eigenvalue_of_DinvA = eig;
+}
+
+extern "C" void rebuild_operator(level_type *level, level_type *fromLevel, double a, double b)
+{
+  if (fromLevel != NULL) {
+    restriction(level, VECTOR_BETA_I, fromLevel, VECTOR_BETA_I, RESTRICT_FACE_I);
+    restriction(level, VECTOR_BETA_J, fromLevel, VECTOR_BETA_J, RESTRICT_FACE_J);
+    restriction(level, VECTOR_BETA_K, fromLevel, VECTOR_BETA_K, RESTRICT_FACE_K);
+  }
+  extrapolate_betas(level);
+  exchange_boundary(level, VECTOR_BETA_I, STENCIL_SHAPE_BOX);
+  exchange_boundary(level, VECTOR_BETA_J, STENCIL_SHAPE_BOX);
+  exchange_boundary(level, VECTOR_BETA_K, STENCIL_SHAPE_BOX);
+  rebuild_operator_blackbox(level, a, b, 4);
+  exchange_boundary(level, VECTOR_DINV, STENCIL_SHAPE_BOX);
+}

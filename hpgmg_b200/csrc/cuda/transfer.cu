@@ -1,0 +1,211 @@
+/*
+ * transfer.cu -- inter-level transfer operators.
+ *
+ *   restriction        operators/restriction.c:6-94 (block kernel), :104-212 (driver)
+ *   interpolation_v2   operators/interpolation_v2.c:8-199, :210-320   (V-cycle prolongation, +=)
+ *   interpolation_v4   operators/interpolation_v4.c:8-265, :276-386   (F-cycle prolongation)
+ *
+ * The kernels walk the device copies of the lists MGBuild produced (mg.c:181-831): one thread
+ * block per list entry; [0] writes into send buffers, [1] is rank-local, [2] unpacks receives.
+ * All arithmetic keeps the reference's association order (bit-exact contract).
+ */
+#include "common.cuh"
+
+void hpgmg_run_copy_list(const DLevel &L, int id, const DList &list);   /* ghost.cu */
+
+/* ---- restriction ------------------------------------------------------------------------------ */
+__global__ void __launch_bounds__(128) restriction_kernel(const DLevel Lc, const int id_c, const DLevel Lf, const int id_f,
+                                                          const blockCopy_type *__restrict__ blocks, const int type)
+{
+  const blockCopy_type B = blocks[blockIdx.x];
+  const double *__restrict__ rd;
+  double *__restrict__ wr;
+  int rj, rk, wj, wk;
+  if (B.read.box >= 0) { rd = Lf.vec(B.read.box, id_f); rj = Lf.jStride; rk = Lf.kStride; }
+  else                 { rd = B.read.ptr;               rj = B.read.jStride; rk = B.read.kStride; }
+  if (B.write.box >= 0) { wr = Lc.vec(B.write.box, id_c); wj = Lc.jStride; wk = Lc.kStride; }
+  else                  { wr = B.write.ptr;               wj = B.write.jStride; wk = B.write.kStride; }
+  rd += B.read.i + B.read.j * rj + B.read.k * rk;
+  wr += B.write.i + B.write.j * wj + B.write.k * wk;
+  const int di = B.dim.i, dj = B.dim.j, cells = di * dj * B.dim.k;
+  for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+    const int i = c % di, j = (c / di) % dj, k = c / (di * dj);
+    const double *r = rd + 2 * i + 2 * j * rj + 2 * k * rk;
+    double v;
+    switch (type) {
+      case RESTRICT_CELL:
+        v = (r[0] + r[1] + r[rj] + r[1 + rj] + r[rk] + r[1 + rk] + r[rj + rk] + r[1 + rj + rk]) * 0.125;
+        break;
+      case RESTRICT_FACE_I:
+        v = (r[0] + r[rj] + r[rk] + r[rj + rk]) * 0.25;
+        break;
+      case RESTRICT_FACE_J:
+        v = (r[0] + r[1] + r[rk] + r[1 + rk]) * 0.25;
+        break;
+      default: /* RESTRICT_FACE_K */
+        v = (r[0] + r[1] + r[rj] + r[1 + rj]) * 0.25;
+        break;
+    }
+    wr[i + j * wj + k * wk] = v;
+  }
+}
+
+static void run_restriction_list(level_type *level_c, int id_c, level_type *level_f, int id_f, const DList &list, int type)
+{
+  if (list.n <= 0) return;
+  /* a rank that owns no coarse boxes still packs for others: give the kernel a valid (empty) DLevel */
+  LAUNCH(restriction_kernel, list.n, 128, 0, dl_of(level_c), id_c, dl_of(level_f), id_f, list.blocks, type);
+}
+
+extern "C" void restriction(level_type *level_c, int id_c, level_type *level_f, int id_f, int restrictionType)
+{
+  hpgmg_device_level *Df = level_f->dev, *Dc = level_c->dev;
+  communicator_type *Cf = &level_f->restriction[restrictionType], *Cc = &level_c->restriction[restrictionType];
+  const int remote = (Cf->num_sends > 0) || (Cc->num_recvs > 0);
+  if (remote) {
+    run_restriction_list(level_c, id_c, level_f, id_f, Df->restriction[restrictionType][0], restrictionType);   /* pack */
+    hpgmg_comm_transfer(level_f, Cf, level_c, Cc, 0x5);
+  }
+  run_restriction_list(level_c, id_c, level_f, id_f, Df->restriction[restrictionType][1], restrictionType);     /* local */
+  if (remote) {
+    hpgmg_comm_transfer_wait(level_f, Cf, level_c, Cc);
+    hpgmg_run_copy_list(Dc->L, id_c, Dc->restriction[restrictionType][2]);                                      /* unpack */
+  }
+}
+
+/* ---- interpolation ---------------------------------------------------------------------------- */
+/* 1-D volume-averaged prolongation of one coarse cell into its two children.
+ * quadratic (v2): lo = c0 + 1/8 (c- - c+),  hi = c0 - 1/8 (c- - c+)
+ * quartic  (v4): lo = c0 + 22/128 (c-1 - c+1) + -3/128 (c-2 - c+2),  hi = c0 - ... - ...            */
+__device__ __forceinline__ void prolong3(const double cm, const double c0, const double cp, double &lo, double &hi)
+{
+  const double c1 = 1.0 / 8.0;
+  lo = (c0 + c1 * (cm - cp));
+  hi = (c0 - c1 * (cm - cp));
+}
+__device__ __forceinline__ void prolong5(const double cmm, const double cm, const double c0, const double cp, const double cpp, double &lo, double &hi)
+{
+  const double c2 = -3.0 / 128.0;
+  const double c1 = 22.0 / 128.0;
+  lo = (c0 + c1 * (cm - cp) + c2 * (cmm - cpp));
+  hi = (c0 - c1 * (cm - cp) - c2 * (cmm - cpp));
+}
+
+template <int W>   /* W = 3 (v2) or 5 (v4): stencil width per axis */
+__global__ void __launch_bounds__(128) interpolation_kernel(const DLevel Lf, const int id_f, const double prescale,
+                                                            const DLevel Lc, const int id_c,
+                                                            const blockCopy_type *__restrict__ blocks, const int force_zero_prescale)
+{
+  constexpr int R = W / 2;
+  const blockCopy_type B = blocks[blockIdx.x];
+  const double *__restrict__ rd;
+  double *__restrict__ wr;
+  int rj, rk, wj, wk;
+  if (B.read.box >= 0) { rd = Lc.vec(B.read.box, id_c); rj = Lc.jStride; rk = Lc.kStride; }
+  else                 { rd = B.read.ptr;               rj = B.read.jStride; rk = B.read.kStride; }
+  if (B.write.box >= 0) { wr = Lf.vec(B.write.box, id_f); wj = Lf.jStride; wk = Lf.kStride; }
+  else                  { wr = B.write.ptr;               wj = B.write.jStride; wk = B.write.kStride; }
+  const double ps = force_zero_prescale ? 0.0 : prescale;
+  const int di = B.dim.i, dj = B.dim.j, cells = di * dj * B.dim.k;
+  for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+    const int ii = c % di, jj = (c / di) % dj, kk = c / (di * dj);
+    const double *r = rd + (ii + B.read.i) + (jj + B.read.j) * rj + (kk + B.read.k) * rk;
+    /* pass 1: along i  -> fi[2][W][W]   (fine i, coarse j, coarse k) */
+    double fi[2][W][W];
+#pragma unroll
+    for (int K = 0; K < W; K++)
+#pragma unroll
+    for (int J = 0; J < W; J++) {
+      const double *p = r + (J - R) * rj + (K - R) * rk;
+      if constexpr (W == 3) prolong3(p[-1], p[0], p[1], fi[0][J][K], fi[1][J][K]);
+      else        prolong5(p[-2], p[-1], p[0], p[1], p[2], fi[0][J][K], fi[1][J][K]);
+    }
+    /* pass 2: along j  -> fj[2][2][W]   (fine i, fine j, coarse k) */
+    double fj[2][2][W];
+#pragma unroll
+    for (int K = 0; K < W; K++)
+#pragma unroll
+    for (int I = 0; I < 2; I++) {
+      if constexpr (W == 3) prolong3(fi[I][0][K], fi[I][1][K], fi[I][2][K], fj[I][0][K], fj[I][1][K]);
+      else        prolong5(fi[I][0][K], fi[I][1][K], fi[I][2][K], fi[I][3][K], fi[I][W - 1][K], fj[I][0][K], fj[I][1][K]);
+    }
+    /* pass 3: along k and commit */
+    double *w = wr + (2 * ii + B.write.i) + (2 * jj + B.write.j) * wj + (2 * kk + B.write.k) * wk;
+#pragma unroll
+    for (int J = 0; J < 2; J++)
+#pragma unroll
+    for (int I = 0; I < 2; I++) {
+      double lo, hi;
+      if constexpr (W == 3) prolong3(fj[I][J][0], fj[I][J][1], fj[I][J][2], lo, hi);
+      else        prolong5(fj[I][J][0], fj[I][J][1], fj[I][J][2], fj[I][J][3], fj[I][J][W - 1], lo, hi);
+      double *w0 = w + I + J * wj;
+      w0[0]  = ps * w0[0] + lo;
+      w0[wk] = ps * w0[wk] + hi;
+    }
+  }
+}
+
+/* fine-level unpack of prolonged data received from another rank: write = prescale*write + recv
+ * (IncrementBlock, blockCopy.c:108-156) */
+__global__ void __launch_bounds__(128) increment_blocks_kernel(const DLevel L, const int id, const double prescale, const blockCopy_type *__restrict__ blocks)
+{
+  const blockCopy_type B = blocks[blockIdx.x];
+  const double *__restrict__ rd;
+  double *__restrict__ wr;
+  int rj, rk, wj, wk;
+  if (B.read.box >= 0) { rd = L.vec(B.read.box, id); rj = L.jStride; rk = L.kStride; }
+  else                 { rd = B.read.ptr;            rj = B.read.jStride; rk = B.read.kStride; }
+  if (B.write.box >= 0) { wr = L.vec(B.write.box, id); wj = L.jStride; wk = L.kStride; }
+  else                  { wr = B.write.ptr;            wj = B.write.jStride; wk = B.write.kStride; }
+  rd += B.read.i + B.read.j * rj + B.read.k * rk;
+  wr += B.write.i + B.write.j * wj + B.write.k * wk;
+  const int di = B.dim.i, dj = B.dim.j, cells = di * dj * B.dim.k;
+  for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+    const int i = c % di, j = (c / di) % dj, k = c / (di * dj);
+    double *w = wr + i + j * wj + k * wk;
+    w[0] = prescale * w[0] + rd[i + j * rj + k * rk];
+  }
+}
+
+template <int W>
+static void interpolation_driver(level_type *level_f, int id_f, double prescale_f, level_type *level_c, int id_c)
+{
+  hpgmg_device_level *Df = level_f->dev, *Dc = level_c->dev;
+  communicator_type *Cc = &level_c->interpolation, *Cf = &level_f->interpolation;
+  const int remote = (Cc->num_sends > 0) || (Cf->num_recvs > 0);
+  if (remote) {
+    const DList &pack = Dc->interpolation[0];
+    if (pack.n > 0) LAUNCH(interpolation_kernel<W>, pack.n, 128, 0, Df->L, id_f, 0.0, Dc->L, id_c, pack.blocks, 1);
+    hpgmg_comm_transfer(level_c, Cc, level_f, Cf, 0x7);
+  }
+  const DList &local = Dc->interpolation[1];
+  if (local.n > 0) LAUNCH(interpolation_kernel<W>, local.n, 128, 0, Df->L, id_f, prescale_f, Dc->L, id_c, local.blocks, 0);
+  if (remote) {
+    hpgmg_comm_transfer_wait(level_c, Cc, level_f, Cf);
+    const DList &unpack = Df->interpolation[2];
+    if (unpack.n > 0) LAUNCH(increment_blocks_kernel, unpack.n, 128, 0, Df->L, id_f, prescale_f, unpack.blocks);
+  }
+}
+
+extern "C" void interpolation_v2(level_type *level_f, int id_f, double prescale_f, level_type *level_c, int id_c)
+{
+  exchange_boundary(level_c, id_c, STENCIL_SHAPE_BOX);
+  apply_BCs_v2(level_c, id_c, STENCIL_SHAPE_BOX);
+  interpolation_driver<3>(level_f, id_f, prescale_f, level_c, id_c);
+}
+
+extern "C" void interpolation_v4(level_type *level_f, int id_f, double prescale_f, level_type *level_c, int id_c)
+{
+  exchange_boundary(level_c, id_c, STENCIL_SHAPE_BOX);
+  apply_BCs_v4(level_c, id_c, STENCIL_SHAPE_BOX);
+  interpolation_driver<5>(level_f, id_f, prescale_f, level_c, id_c);
+}
+
+extern "C" void interpolation_vcycle(level_type *level_f, int id_f, double prescale_f, level_type *level_c, int id_c)
+{
+  interpolation_v2(level_f, id_f, prescale_f, level_c, id_c);
+}
+extern "C" void interpolation_fcycle(level_type *level_f, int id_f, double prescale_f, level_type *level_c, int id_c)
+{
+  interpolation_v4(level_f, id_f, prescale_f, level_c, id_c);
+}

@@ -1,0 +1,81 @@
+/*
+ * runtime.h -- internal seam between the C host code (level.c, mg.c, solvers.c, problem.c) and
+ * the CUDA translation units.  Nothing here is part of the public C-ABI (see include/).
+ *
+ * The host code never dereferences vector or buffer memory; it goes through these calls.
+ */
+#ifndef HPGMG_B200_RUNTIME_H
+#define HPGMG_B200_RUNTIME_H
+
+#include <stddef.h>
+#include "hpgmg_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* process-wide settings (runtime.cu) */
+int  hpgmg_rt_verbose(void);          /* print reference-style progress lines?            */
+int  hpgmg_rt_smoother(void);
+int  hpgmg_rt_use_graphs(void);
+int  hpgmg_rt_profile(void);
+double hpgmg_rt_wtime(void);          /* host wall clock, seconds                         */
+
+/* device memory (zero-filled) and copies, all ordered on the compute stream */
+void *hpgmg_rt_alloc_zero(size_t bytes);
+void  hpgmg_rt_free(void *p);
+void  hpgmg_rt_copy_d2d(void *dst, const void *src, size_t bytes);
+void  hpgmg_rt_copy_h2d(void *dst, const void *src, size_t bytes);
+void  hpgmg_rt_copy_d2h(void *dst, const void *src, size_t bytes);
+void  hpgmg_rt_sync(void);
+
+/* device mirror of a level's lists (device_level.cu) */
+void hpgmg_device_level_create(level_type *level);            /* after lists of create_level exist */
+void hpgmg_device_level_rebind_vectors(level_type *level);    /* after create_vectors() regrew     */
+void hpgmg_device_level_upload_transfer_lists(level_type *level); /* after build_restriction/interpolation */
+void hpgmg_device_level_destroy(level_type *level);
+
+/* CUDA-graph capture of a whole solve (graphs.cu).  `key` identifies the recorded sequence.
+ * begin returns 1 if the caller must now enqueue the work (recording), 0 if a recorded graph was
+ * replayed and the caller must skip enqueueing. */
+int  hpgmg_graph_begin(const void *owner, long long key);
+void hpgmg_graph_end(const void *owner, long long key);
+void hpgmg_graph_drop_all(const void *owner);
+
+/* device-side scalars: results of norm/dot that stay on the GPU inside a captured solve */
+double *hpgmg_rt_scalar_slots(void);                  /* device array of HPGMG_NUM_SCALARS doubles */
+void    hpgmg_rt_read_scalars(double *host, int first, int count); /* sync + copy */
+#define HPGMG_NUM_SCALARS 64
+#define HPGMG_SLOT_NORM_F   0
+#define HPGMG_SLOT_NORM_R   1
+#define HPGMG_SLOT_SCRATCH  8
+
+/* async reductions that leave their result in a scalar slot (no host sync) */
+void hpgmg_norm_async(level_type *level, int id_a, int slot);
+
+/* on-device bottom solver; returns 0 if the level is not eligible (caller falls back to the
+ * host-driven BiCGStab in solvers.c) */
+int  hpgmg_bicgstab_device(level_type *level, int x_id, int R_id, double a, double b, double rtol);
+
+void hpgmg_bicgstab_collect_iterations(level_type *level);
+
+/* inter-GPU plumbing (comm.cu): no-ops on a single rank */
+int    hpgmg_comm_rank(void);
+int    hpgmg_comm_size(void);
+void   hpgmg_comm_barrier(void);
+double hpgmg_comm_allreduce_max(level_type *level, double v);
+double hpgmg_comm_allreduce_sum(level_type *level, double v);
+void   hpgmg_comm_allreduce_slot_max(level_type *level, int slot);
+void   hpgmg_comm_exchange(level_type *level, communicator_type *C, int tag);
+void   hpgmg_comm_exchange_wait(level_type *level, communicator_type *C);
+void   hpgmg_comm_transfer(level_type *level_send, communicator_type *Cs, level_type *level_recv, communicator_type *Cr, int tag);
+void   hpgmg_comm_transfer_wait(level_type *level_send, communicator_type *Cs, level_type *level_recv, communicator_type *Cr);
+
+/* event timing of a solve body */
+void hpgmg_rt_timer_start(void);
+void hpgmg_rt_timer_stop(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

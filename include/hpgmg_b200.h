@@ -1,0 +1,91 @@
+/*
+ * hpgmg_b200.h -- extension C-ABI of the B200 build (everything the reference API cannot say
+ * because it assumes host memory and compile-time variant selection).
+ *
+ * Plain C, plain pointers and sizes; no CUDA or torch types cross this boundary.  The Python
+ * host layer (hpgmg_b200/api.py) binds these with ctypes; a C caller links libhpgmg_b200.so.
+ *
+ * Reference counterparts are cited per function; where there is none the reason is given.
+ */
+#ifndef HPGMG_B200_H
+#define HPGMG_B200_H
+
+#include "hpgmg_defines.h"
+#include "hpgmg_level.h"
+#include "hpgmg_operators.h"
+#include "hpgmg_solvers.h"
+#include "hpgmg_mg.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- runtime ------------------------------------------------------------------------------
+ * The reference has no device to select (hpgmg-fv.c:103-140 only does MPI_Init).  One process
+ * drives one GPU; call once before create_level().  Returns 0 on success; on a machine without
+ * a usable sm_100 device it prints the CUDA error and returns non-zero -- there is no CPU path. */
+int  hpgmg_b200_init(int device_ordinal);
+void hpgmg_b200_finalize(void);
+void hpgmg_b200_sync(void);                      /* drain the compute stream                    */
+const char *hpgmg_b200_backend(void);            /* "cuda-sm_100a" (or "cpu-emulation" in the
+                                                    kernel-debug harness under tests/)          */
+
+/* ---- variant selection ----------------------------------------------------------------------
+ * The reference picks the smoother at compile time (-DUSE_GSRB | -DUSE_CHEBY,
+ * operators.fv4.c:176-195, hpgmgconf.py:114-126).  Here it is a runtime switch. */
+#define HPGMG_SMOOTHER_GSRB  0                   /* 3x red-black = 6 sweeps   (NUM_SMOOTHS 3)   */
+#define HPGMG_SMOOTHER_CHEBY 1                   /* one degree-6 polynomial   (CHEBYSHEV_DEGREE) */
+void hpgmg_b200_set_smoother(int which);
+int  hpgmg_b200_get_smoother(void);
+
+/* 0: silent; 1: the reference's progress lines on stdout (default, rank 0 only). */
+void hpgmg_b200_set_verbose(int on);
+
+/* 1 (default): FMGSolve/MGSolve record their kernel sequence once per (level,ids) into a CUDA
+ * graph and replay it.  0: plain stream launches (used by the per-operator timers). */
+void hpgmg_b200_use_graphs(int on);
+
+/* 1: each operator synchronises and adds its device time to level->timers.* like the reference's
+ * getTime() brackets (e.g. gsrb.c:37,130).  0 (default): timers only hold MGSolve totals. */
+void hpgmg_b200_profile_operators(int on);
+
+/* ---- moving data across the boundary ------------------------------------------------------
+ * The reference reads box arrays directly (e.g. problem.fv.c:129-135).  Device memory needs an
+ * explicit copy: `host` holds box->volume doubles in the box's own [k][j][i] layout, ghosts
+ * included.  The *_async forms require pinned host memory to overlap; all go through the
+ * compute stream so they are ordered with the operators. */
+void hpgmg_download_box_vector(level_type *level, int box, int id, double *host);
+void hpgmg_upload_box_vector(level_type *level, int box, int id, const double *host);
+void *hpgmg_b200_host_alloc_pinned(size_t bytes);
+void  hpgmg_b200_host_free_pinned(void *p);
+
+/* FMGSolve with HOST buffers (the end-to-end call of bench.py): uploads f (num_my_boxes x volume
+ * doubles, box-major) into F_id, zeroes u_id, runs FMGSolve (mg.c:1237), downloads u_id into u.
+ * Returns the F-cycle residual max-norm (the number mg.c:1325-1329 prints). */
+double hpgmg_fmg_solve_host(mg_type *all_grids, int onLevel, int u_id, int F_id, double a, double b,
+                            double rtol, const double *f_host, double *u_host);
+
+/* Norms of the last FMGSolve/MGSolve on this hierarchy: ||F||, ||r|| after the F-cycle (or
+ * last V-cycle).  The reference only prints them (mg.c:1325-1329); tests need the values. */
+double hpgmg_last_norm_of_F(const mg_type *all_grids);
+double hpgmg_last_norm_of_residual(const mg_type *all_grids);
+
+/* ---- evidence ------------------------------------------------------------------------------ */
+unsigned long long hpgmg_b200_kernel_launches(void);  /* kernels enqueued so far (graph replays count their nodes) */
+double hpgmg_b200_device_seconds_last_solve(void);    /* CUDA-event time of the last FMGSolve/MGSolve body */
+
+/* ---- multi-GPU plumbing -----------------------------------------------------------------------
+ * The reference talks MPI (exchange_boundary.c:33-97, restriction.c:128-192, misc.c:276,324).
+ * Here ranks are processes launched by torchrun; the host layer provides two callbacks (backed
+ * by torch.distributed) that are used only at SETUP time: an allgather of small byte blobs (to
+ * swap CUDA-IPC handles) and a barrier.  The timed path never calls back into Python: halo
+ * faces are stored straight into the neighbour GPU's receive buffer through the peer mapping and
+ * completion is signalled with a flag in the same mapping. */
+typedef void (*hpgmg_allgather_fn)(const void *send, void *recv, size_t bytes_per_rank, void *ctx);
+typedef void (*hpgmg_barrier_fn)(void *ctx);
+void hpgmg_b200_set_comm(int my_rank, int num_ranks, hpgmg_allgather_fn allgather, hpgmg_barrier_fn barrier, void *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
