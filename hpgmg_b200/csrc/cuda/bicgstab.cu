@@ -26,7 +26,7 @@ struct BottomArgs {
   int nbc;
   int x_id, R_id;
   double a, b, h2inv, rtol;
-  int *iters;
+  double *iters;                /* device scalar slot: iterations are added to it */
 };
 
 struct BottomCtx {
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(BOTTOM_THREADS) bicgstab_kernel(const BottomAr
     b_add(C, p, 1.0, r, beta, VECTOR_TEMP);
     r_dot_r0 = r_dot_r0_new;
   }
-  if (threadIdx.x == 0) atomicAdd(A.iters, j);
+  if (threadIdx.x == 0) atomicAdd(A.iters, (double)j);
 }
 
 /* Returns 1 if the solve was enqueued on the device, 0 if the level is not eligible (more than one
@@ -221,19 +221,8 @@ extern "C" int hpgmg_bicgstab_device(level_type *level, int x_id, int R_id, doub
   A.x_id = x_id;  A.R_id = R_id;  A.a = a;  A.b = b;
   A.h2inv = 1.0 / (level->h * level->h);
   A.rtol = rtol;
-  A.iters = D->krylov_iters;
+  A.iters = hpgmg_rt_scalar_slots() + HPGMG_SLOT_KRYLOV;
   LAUNCH(bicgstab_kernel, 1, BOTTOM_THREADS, 0, A);
   return 1;
 }
 
-/* fold the device iteration counter into level->Krylov_iterations (called after a solve has synchronised) */
-extern "C" void hpgmg_bicgstab_collect_iterations(level_type *level)
-{
-  hpgmg_device_level *D = level->dev;
-  if (!D || !D->krylov_iters) return;
-  int it = 0;
-  CUDA_CHECK(cudaMemcpyAsync(&it, D->krylov_iters, sizeof(int), cudaMemcpyDeviceToHost, g_stream));
-  CUDA_CHECK(cudaMemsetAsync(D->krylov_iters, 0, sizeof(int), g_stream));
-  CUDA_CHECK(cudaStreamSynchronize(g_stream));
-  level->Krylov_iterations += it;
-}

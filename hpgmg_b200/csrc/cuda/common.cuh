@@ -25,8 +25,10 @@ void hpgmg_cuda_check(cudaError_t e, const char *what, const char *file, int lin
 #define CUDA_CHECK(x) hpgmg_cuda_check((x), #x, __FILE__, __LINE__)
 
 /* launch on the compute stream and count it */
+void hpgmg_refuse_launch(const char *kernel);
 #define LAUNCH(kernel, grid, block, smem, ...)                                  \
   do {                                                                          \
+    if (hpgmg_rt_layout_only()) hpgmg_refuse_launch(#kernel);                   \
     kernel<<<(grid), (block), (smem), g_stream>>>(__VA_ARGS__);                 \
     g_launches++;                                                               \
     CUDA_CHECK(cudaGetLastError());                                             \
@@ -63,7 +65,6 @@ struct hpgmg_device_level {
   double *tile_partials;                        /* scratch for dot/mean: one double per compute tile */
   blockCopy_type *tiles;                        /* device copy of level->my_blocks                  */
   int     ntiles;
-  int    *krylov_iters;                         /* device counter bumped by the on-device BiCGStab  */
 };
 
 static inline const DLevel &dl_of(const level_type *level) { return level->dev->L; }

@@ -8,10 +8,10 @@
 
 static void upload_list(DList *dst, const blockCopy_type *src, int n)
 {
-  if (dst->blocks) { CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaFree(dst->blocks)); }
+  if (dst->blocks && !hpgmg_rt_layout_only()) { CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaFree(dst->blocks)); }
   dst->blocks = NULL;
   dst->n = n;
-  if (n <= 0) return;
+  if (n <= 0 || hpgmg_rt_layout_only()) return;
   CUDA_CHECK(cudaMalloc(&dst->blocks, (size_t)n * sizeof(blockCopy_type)));
   CUDA_CHECK(cudaMemcpyAsync(dst->blocks, src, (size_t)n * sizeof(blockCopy_type), cudaMemcpyHostToDevice, g_stream));
   CUDA_CHECK(cudaStreamSynchronize(g_stream));
@@ -45,6 +45,7 @@ extern "C" void hpgmg_device_level_create(level_type *level)
   level->dev = D;
   hpgmg_device_level_rebind_vectors(level);
 
+  if (hpgmg_rt_layout_only()) return;
   const int nb = level->num_my_boxes;
   if (nb > 0) {
     int *low = (int *)malloc((size_t)nb * 3 * sizeof(int));
@@ -70,8 +71,6 @@ extern "C" void hpgmg_device_level_create(level_type *level)
     CUDA_CHECK(cudaMalloc(&D->tile_partials, (size_t)D->ntiles * sizeof(double)));
     CUDA_CHECK(cudaStreamSynchronize(g_stream));
   }
-  CUDA_CHECK(cudaMalloc(&D->krylov_iters, sizeof(int)));
-  CUDA_CHECK(cudaMemsetAsync(D->krylov_iters, 0, sizeof(int), g_stream));
 }
 
 extern "C" void hpgmg_device_level_upload_transfer_lists(level_type *level)
@@ -88,6 +87,7 @@ extern "C" void hpgmg_device_level_destroy(level_type *level)
 {
   hpgmg_device_level *D = level->dev;
   if (!D) return;
+  if (hpgmg_rt_layout_only()) { free(D); level->dev = NULL; return; }
   CUDA_CHECK(cudaStreamSynchronize(g_stream));
   for (int s = 0; s < STENCIL_MAX_SHAPES; s++) {
     free_list(&D->bc[s]);
@@ -98,7 +98,6 @@ extern "C" void hpgmg_device_level_destroy(level_type *level)
   if (D->low) CUDA_CHECK(cudaFree(D->low));
   if (D->tiles) CUDA_CHECK(cudaFree(D->tiles));
   if (D->tile_partials) CUDA_CHECK(cudaFree(D->tile_partials));
-  if (D->krylov_iters) CUDA_CHECK(cudaFree(D->krylov_iters));
   free(D);
   level->dev = NULL;
 }

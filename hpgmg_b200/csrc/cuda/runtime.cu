@@ -7,8 +7,11 @@
  */
 #include <string.h>
 #include <time.h>
+#include <sys/mman.h>
+#include <map>
 #include <vector>
 
+#include <cuda_profiler_api.h>
 #include "common.cuh"
 
 cudaStream_t g_stream = 0;
@@ -26,6 +29,20 @@ static double *g_scalars_host = NULL;       /* pinned mirror                    
 static cudaEvent_t g_ev0, g_ev1;
 static double g_last_device_seconds = 0.0;
 
+/* Layout-only mode: the host-side data model (decomposition, block lists, level table) can be built
+ * and inspected on a machine without a GPU.  Allocations become inaccessible address-space
+ * reservations (any dereference faults), nothing is copied and every kernel launch aborts -- it is
+ * a way to test the index mapping, not a compute path. */
+static int g_layout_only = 0;
+static std::map<void *, size_t> g_reservations;
+extern "C" void hpgmg_b200_set_layout_only(int on) { g_layout_only = on; }
+extern "C" int  hpgmg_rt_layout_only(void) { return g_layout_only; }
+void hpgmg_refuse_launch(const char *kernel)
+{
+  fprintf(stderr, "hpgmg_b200: kernel %s requested in layout-only mode; compute needs a B200 (no CPU fallback)\n", kernel);
+  abort();
+}
+
 void hpgmg_cuda_check(cudaError_t e, const char *what, const char *file, int line)
 {
   if (e == cudaSuccess) return;
@@ -36,7 +53,7 @@ void hpgmg_cuda_check(cudaError_t e, const char *what, const char *file, int lin
 
 static void require_init(const char *who)
 {
-  if (g_initialised) return;
+  if (g_initialised || g_layout_only) return;
   /* lazy init on device 0 (or HPGMG_B200_DEVICE / LOCAL_RANK) so that a reference-style main()
    * that knows nothing about GPUs still works; failure is fatal -- there is no CPU path */
   int dev = 0;
@@ -116,6 +133,12 @@ extern "C" void *hpgmg_rt_alloc_zero(size_t bytes)
 {
   require_init("alloc");
   if (bytes == 0) bytes = 8;
+  if (g_layout_only) {
+    void *r = mmap(NULL, bytes, PROT_NONE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (r == MAP_FAILED) { fprintf(stderr, "hpgmg_b200: cannot reserve %zu bytes of address space\n", bytes); exit(0); }
+    g_reservations[r] = bytes;
+    return r;
+  }
   void *p = NULL;
   cudaError_t e = cudaMalloc(&p, bytes);
   if (e != cudaSuccess) {
@@ -125,14 +148,24 @@ extern "C" void *hpgmg_rt_alloc_zero(size_t bytes)
   CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, g_stream));
   return p;
 }
-extern "C" void hpgmg_rt_free(void *p) { if (p) { CUDA_CHECK(cudaStreamSynchronize(g_stream)); CUDA_CHECK(cudaFree(p)); } }
+extern "C" void hpgmg_rt_free(void *p)
+{
+  if (!p) return;
+  if (g_layout_only) {
+    std::map<void *, size_t>::iterator it = g_reservations.find(p);
+    if (it != g_reservations.end()) { munmap(p, it->second); g_reservations.erase(it); }
+    return;
+  }
+  CUDA_CHECK(cudaStreamSynchronize(g_stream));
+  CUDA_CHECK(cudaFree(p));
+}
 extern "C" void *MALLOC(size_t size) { return hpgmg_rt_alloc_zero(size); }
 extern "C" void  FREE(void *ptr) { hpgmg_rt_free(ptr); }
 
-extern "C" void hpgmg_rt_copy_d2d(void *dst, const void *src, size_t bytes) { CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_stream)); }
-extern "C" void hpgmg_rt_copy_h2d(void *dst, const void *src, size_t bytes) { CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream)); }
-extern "C" void hpgmg_rt_copy_d2h(void *dst, const void *src, size_t bytes) { CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream)); }
-extern "C" void hpgmg_rt_sync(void) { if (g_initialised) CUDA_CHECK(cudaStreamSynchronize(g_stream)); }
+extern "C" void hpgmg_rt_copy_d2d(void *dst, const void *src, size_t bytes) { if (g_layout_only) return; CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, g_stream)); }
+extern "C" void hpgmg_rt_copy_h2d(void *dst, const void *src, size_t bytes) { if (g_layout_only) return; CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, g_stream)); }
+extern "C" void hpgmg_rt_copy_d2h(void *dst, const void *src, size_t bytes) { if (g_layout_only) return; CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, g_stream)); }
+extern "C" void hpgmg_rt_sync(void) { if (g_initialised && !g_layout_only) CUDA_CHECK(cudaStreamSynchronize(g_stream)); }
 
 extern "C" void *hpgmg_b200_host_alloc_pinned(size_t bytes)
 {
@@ -158,6 +191,10 @@ extern "C" void hpgmg_upload_box_vector(level_type *level, int box, int id, cons
 
 /* ------------------------------------------------------------------------------------------ */
 extern "C" double *hpgmg_rt_scalar_slots(void) { require_init("scalars"); return g_scalars; }
+extern "C" void hpgmg_rt_zero_scalar(int slot)
+{
+  CUDA_CHECK(cudaMemsetAsync(g_scalars + slot, 0, sizeof(double), g_stream));
+}
 extern "C" void hpgmg_rt_read_scalars(double *host, int first, int count)
 {
   CUDA_CHECK(cudaMemcpyAsync(g_scalars_host + first, g_scalars + first, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
@@ -225,6 +262,26 @@ extern "C" double hpgmg_b200_device_seconds_last_solve(void)
   CUDA_CHECK(cudaEventElapsedTime(&ms, g_ev0, g_ev1));
   g_last_device_seconds = 1e-3 * (double)ms;
   return g_last_device_seconds;
+}
+/* bracket a region for `ncu --profile-from-start off` */
+extern "C" void hpgmg_b200_profiler_start(void) { require_init("profiler"); CUDA_CHECK(cudaStreamSynchronize(g_stream)); cudaProfilerStart(); }
+extern "C" void hpgmg_b200_profiler_stop(void) { CUDA_CHECK(cudaStreamSynchronize(g_stream)); cudaProfilerStop(); }
+
+/* event marks on the compute stream for callers that time several calls (bench.py) */
+static cudaEvent_t g_marks[8];
+static int g_marks_ready = 0;
+extern "C" void hpgmg_b200_bench_mark(int idx)
+{
+  require_init("bench mark");
+  if (!g_marks_ready) { for (int i = 0; i < 8; i++) CUDA_CHECK(cudaEventCreate(&g_marks[i])); g_marks_ready = 1; }
+  CUDA_CHECK(cudaEventRecord(g_marks[idx & 7], g_stream));
+}
+extern "C" double hpgmg_b200_bench_elapsed_ms(int from, int to)
+{
+  float ms = 0.f;
+  CUDA_CHECK(cudaEventSynchronize(g_marks[to & 7]));
+  CUDA_CHECK(cudaEventElapsedTime(&ms, g_marks[from & 7], g_marks[to & 7]));
+  return (double)ms;
 }
 extern "C" unsigned long long hpgmg_b200_kernel_launches(void) { return g_launches; }
 

@@ -129,6 +129,14 @@ static void smooth_gsrb(level_type *level, int x_id, int rhs_id, double a, doubl
   }
 }
 
+/* one GSRB sweep kernel alone (no ghost fill): what bench.py times for the roofline line */
+extern "C" void hpgmg_b200_gsrb_sweep(level_type *level, int src_id, int dst_id, int rhs_id, double a, double b, int s)
+{
+  StencilArgs A = {};
+  A.x_id = src_id;  A.rhs_id = rhs_id;  A.out_id = dst_id;  A.a = a;  A.b = b;  A.sweep = s;
+  launch_stencil<OP_GSRB>(level, A);
+}
+
 static void smooth_chebyshev(level_type *level, int x_id, int rhs_id, double a, double b)
 {
   enum { DEGREE = 6 };                               /* CHEBYSHEV_DEGREE (operators.fv4.c:184) */

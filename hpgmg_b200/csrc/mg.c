@@ -417,7 +417,8 @@ void MGBuild(mg_type *MG, level_type *fine, double a, double b, int minCoarseGri
   }
 
   if (chatty) fprintf(stdout, "\n");
-  for (int l = 1; l < MG->num_levels; l++) rebuild_operator(MG->levels[l], MG->levels[l - 1], a, b);
+  if (!hpgmg_rt_layout_only())        /* layout-only mode builds the lists but cannot run kernels */
+    for (int l = 1; l < MG->num_levels; l++) rebuild_operator(MG->levels[l], MG->levels[l - 1], a, b);
   if (chatty) fprintf(stdout, "\n");
 
   for (int l = 0; l < MG->num_levels; l++) {
@@ -576,6 +577,7 @@ void FMGSolve(mg_type *MG, int onLevel, int u_id, int F_id, double a, double b, 
   const long long key = solve_key(1, onLevel, u_id, F_id, a, b);
   hpgmg_rt_timer_start();
   if (!capturable || hpgmg_graph_begin(MG, key)) {
+    hpgmg_rt_zero_scalar(HPGMG_SLOT_KRYLOV);
     enqueue_fcycle(MG, onLevel, e_id, R_id, F_id, a, b);
     enqueue_residual_norm(L, e_id, F_id, a, b);
     if (capturable) hpgmg_graph_end(MG, key);
@@ -583,9 +585,10 @@ void FMGSolve(mg_type *MG, int onLevel, int u_id, int F_id, double a, double b, 
   hpgmg_rt_timer_stop();
   count_vcycle_visits(MG, onLevel);
 
-  double s[2];
-  hpgmg_rt_read_scalars(s, HPGMG_SLOT_NORM_F, 2);         /* the solve's only synchronisation */
+  double s[3];
+  hpgmg_rt_read_scalars(s, HPGMG_SLOT_NORM_F, 3);         /* the solve's only synchronisation */
   double norm_of_F = s[0], norm_of_residual = s[1];
+  MG->levels[MG->num_levels - 1]->Krylov_iterations += (int)s[2];   /* counted on the device by the bottom solver */
   if (chatty) fprintf(stdout, "f-cycle     norm=%1.15e  rel=%1.15e  ", norm_of_residual, norm_of_residual / norm_of_F);
 
   /* optional post-F V-cycles until converged (UNLIMIT_FMG_ITERATIONS) */

@@ -19,6 +19,7 @@ int  hpgmg_rt_verbose(void);          /* print reference-style progress lines?  
 int  hpgmg_rt_smoother(void);
 int  hpgmg_rt_use_graphs(void);
 int  hpgmg_rt_profile(void);
+int  hpgmg_rt_layout_only(void);   /* host data model only: no device, kernels refuse to launch */
 double hpgmg_rt_wtime(void);          /* host wall clock, seconds                         */
 
 /* device memory (zero-filled) and copies, all ordered on the compute stream */
@@ -48,6 +49,7 @@ void    hpgmg_rt_read_scalars(double *host, int first, int count); /* sync + cop
 #define HPGMG_NUM_SCALARS 64
 #define HPGMG_SLOT_NORM_F   0
 #define HPGMG_SLOT_NORM_R   1
+#define HPGMG_SLOT_KRYLOV   2   /* bottom-solver iterations of the current solve (as a double) */
 #define HPGMG_SLOT_SCRATCH  8
 
 /* async reductions that leave their result in a scalar slot (no host sync) */
@@ -57,7 +59,7 @@ void hpgmg_norm_async(level_type *level, int id_a, int slot);
  * host-driven BiCGStab in solvers.c) */
 int  hpgmg_bicgstab_device(level_type *level, int x_id, int R_id, double a, double b, double rtol);
 
-void hpgmg_bicgstab_collect_iterations(level_type *level);
+void hpgmg_rt_zero_scalar(int slot);                  /* async, capturable */
 
 /* inter-GPU plumbing (comm.cu): no-ops on a single rank */
 int    hpgmg_comm_rank(void);

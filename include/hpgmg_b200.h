@@ -49,6 +49,19 @@ void hpgmg_b200_use_graphs(int on);
  * getTime() brackets (e.g. gsrb.c:37,130).  0 (default): timers only hold MGSolve totals. */
 void hpgmg_b200_profile_operators(int on);
 
+/* 1: build only the host-side data model (decomposition, block lists, level table): allocations
+ * become inaccessible address-space reservations and any kernel launch aborts.  Lets the index
+ * mapping be diffed against the reference on a machine without a GPU; it is not a compute path. */
+void hpgmg_b200_set_layout_only(int on);
+
+/* The reference's -DUNLIMIT_FMG_ITERATIONS (mg.c:1243-1247): up to n V-cycles after the F-cycle
+ * until ||r||/||f|| < rtol.  Default 0, as in the benchmark. */
+void hpgmg_b200_set_fmg_post_vcycles(int n);
+
+/* values richardson_error() last printed (mg.c:1128-1130) */
+double hpgmg_last_richardson_error(void);
+double hpgmg_last_richardson_order(void);
+
 /* ---- moving data across the boundary ------------------------------------------------------
  * The reference reads box arrays directly (e.g. problem.fv.c:129-135).  Device memory needs an
  * explicit copy: `host` holds box->volume doubles in the box's own [k][j][i] layout, ghosts
@@ -74,16 +87,26 @@ double hpgmg_last_norm_of_residual(const mg_type *all_grids);
 unsigned long long hpgmg_b200_kernel_launches(void);  /* kernels enqueued so far (graph replays count their nodes) */
 double hpgmg_b200_device_seconds_last_solve(void);    /* CUDA-event time of the last FMGSolve/MGSolve body */
 
+/* event marks on the library's compute stream, for timing several calls from outside (bench.py) */
+void   hpgmg_b200_bench_mark(int idx);                /* idx 0..7 */
+double hpgmg_b200_bench_elapsed_ms(int from_idx, int to_idx);
+/* cudaProfilerStart/Stop around a region, for `ncu --profile-from-start off` captures */
+void   hpgmg_b200_profiler_start(void);
+void   hpgmg_b200_profiler_stop(void);
+/* exactly one GSRB sweep kernel of smooth() (gsrb.c:41-129), without the ghost fill: dst = sweep s of src */
+void   hpgmg_b200_gsrb_sweep(level_type *level, int src_id, int dst_id, int rhs_id, double a, double b, int s);
+
 /* ---- multi-GPU plumbing -----------------------------------------------------------------------
  * The reference talks MPI (exchange_boundary.c:33-97, restriction.c:128-192, misc.c:276,324).
- * Here ranks are processes launched by torchrun; the host layer provides two callbacks (backed
- * by torch.distributed) that are used only at SETUP time: an allgather of small byte blobs (to
- * swap CUDA-IPC handles) and a barrier.  The timed path never calls back into Python: halo
- * faces are stored straight into the neighbour GPU's receive buffer through the peer mapping and
- * completion is signalled with a flag in the same mapping. */
+ * Here ranks are processes launched by torchrun, one per GPU.  The host layer provides two
+ * callbacks (backed by torch.distributed) that are used only at SETUP time: an allgather of small
+ * byte blobs (to distribute the NCCL unique id) and a barrier.  The timed path never calls back
+ * into Python: halo and inter-level messages are grouped ncclSend/ncclRecv on the compute stream,
+ * norms are an 8-byte ncclAllReduce on a device scalar. */
 typedef void (*hpgmg_allgather_fn)(const void *send, void *recv, size_t bytes_per_rank, void *ctx);
 typedef void (*hpgmg_barrier_fn)(void *ctx);
 void hpgmg_b200_set_comm(int my_rank, int num_ranks, hpgmg_allgather_fn allgather, hpgmg_barrier_fn barrier, void *ctx);
+void hpgmg_b200_comm_finalize(void);
 
 #ifdef __cplusplus
 }
