@@ -2,7 +2,7 @@
 
 The layouts equal the reference's no-MPI build (finite-volume/source/level.h:65-200, mg.h:22-33), so the
 same classes describe a level built by libhpgmg_b200.so (vectors are DEVICE pointers) and one built by
-the reference compiled under oracle/_ref (vectors are host pointers); only the trailing ``dev`` field is
+the reference itself compiled as a host library by the test suite (vectors are host pointers); only the trailing ``dev`` field is
 ours.  Used by the host layer (api.py) and by the tests to diff block lists entry by entry.
 """
 import ctypes as C

@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Regenerate tests/golden/goldens.json from the UNMODIFIED reference (oracle/_ref, built by
+oracle/Makefile from /root/reference/finite-volume/source with gcc -O2 -fopenmp, no FMA).
+
+  python tests/golden/make_goldens.py
+
+Recorded per solve configuration (`hpgmg-fv <log2_box_dim> <boxes>` on one rank; an N-rank run has
+the same boxes and therefore the same numbers): the F-cycle residual norms of the
+driver's three Richardson solves (hpgmg-fv.c:357-365), ||error|| and the observed order
+(mg.c:1128-1130), the Gershgorin bound per level (rebuild.c:204) and the bottom-solver iteration
+count.  Recorded per decomposition (ranks N, rank r): counts and digests of every block list of
+every level plus the send/recv tables -- the "index mapping" the port must reproduce bit for bit.
+"""
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import oracle_bindings as ob  # noqa: E402
+import hpgmg_b200.api as api  # noqa: E402
+
+SOLVES = [(4, 1, False), (5, 1, False), (6, 1, False), (4, 8, False), (5, 8, False), (6, 8, False), (7, 8, False),
+          (4, 27, False), (5, 27, False), (5, 64, False),
+          (5, 1, True), (5, 8, True), (6, 8, True), (5, 27, True)]
+DECOMPOSITIONS = [(5, 8, 1), (5, 8, 2), (5, 8, 4), (5, 8, 8), (4, 1, 1), (6, 8, 1), (6, 8, 8), (4, 3, 9)]
+
+
+def solve_record(log2, boxes, cheby):
+    H = ob.RefHierarchy(log2, boxes, cheby=cheby)
+    H.call("MGResetTimers", H.mg)          # the reference never initialises Krylov_iterations otherwise
+    norms = []
+    for l in range(3):
+        if l > 0:
+            H.call("restriction", H.level(l), api.VECTOR_F, H.level(l - 1), api.VECTOR_F, api.RESTRICT_CELL)
+        norms.append(H.fmg_solve(l))
+    # richardson_error (mg.c:1113-1131) prints only: redo its arithmetic with the same calls
+    L1, L2, L0 = H.level(1), H.level(2), H.level(0)
+    H.call("restriction", L1, api.VECTOR_TEMP, L0, api.VECTOR_U, api.RESTRICT_CELL)
+    H.call("restriction", L2, api.VECTOR_TEMP, L1, api.VECTOR_U, api.RESTRICT_CELL)
+    H.call("add_vectors", L1, api.VECTOR_TEMP, 1.0, api.VECTOR_U, -1.0, api.VECTOR_TEMP)
+    H.call("add_vectors", L2, api.VECTOR_TEMP, 1.0, api.VECTOR_U, -1.0, api.VECTOR_TEMP)
+    e2h, e4h = H.call("norm", L1, api.VECTOR_TEMP), H.call("norm", L2, api.VECTOR_TEMP)
+    import math
+    rec = {"norms": norms, "error": e2h, "order": math.log(e4h / e2h) / math.log(2),
+           "eigs": [H.level(l).contents.dominant_eigenvalue_of_DinvA for l in range(H.num_levels)],
+           "dims": [H.level(l).contents.dim.i for l in range(H.num_levels)],
+           "box_dims": [H.level(l).contents.box_dim for l in range(H.num_levels)],
+           "krylov_iterations_3_solves": H.level(H.num_levels - 1).contents.Krylov_iterations,
+           "norm_of_F": H.call("norm", L0, api.VECTOR_F)}
+    return rec
+
+
+def decomposition_record(log2, boxes_per_rank, ranks):
+    out = []
+    for r in range(ranks):
+        H = ob.RefHierarchy(log2, boxes_per_rank, my_rank=r, num_ranks=ranks, build_operator=False)
+        H.build_lists_only()
+        out.append([ob.level_list_summary(H.level(l)) for l in range(H.num_levels)])
+    return out
+
+
+def main():
+    assert ob.have_ref() and ob.have_ref(True), "build oracle/_ref first: make -C oracle ref"
+    G = {"generator": "tests/golden/make_goldens.py", "reference_flags": "gcc -O2 -fopenmp -std=gnu99 -DUSE_BICGSTAB=1 -DUSE_SUBCOMM=1 -DUSE_FCYCLES=1 -DUSE_{GSRB,CHEBY}=1 (x86-64 baseline: no FMA)",
+         "solves": {}, "decompositions": {}}
+    for log2, boxes, cheby in SOLVES:
+        key = f"{log2} {boxes} {'cheby' if cheby else 'gsrb'}"
+        print("solve", key, flush=True, file=sys.stderr)
+        G["solves"][key] = solve_record(log2, boxes, cheby)
+    for log2, bpr, ranks in DECOMPOSITIONS:
+        key = f"{log2} {bpr} x{ranks}"
+        print("decomposition", key, flush=True, file=sys.stderr)
+        G["decompositions"][key] = decomposition_record(log2, bpr, ranks)
+    with open(os.path.join(HERE, "goldens.json"), "w") as f:
+        json.dump(G, f, indent=0, separators=(",", ":"))
+    print("wrote goldens.json", file=sys.stderr)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,300 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C-ABI, against
+  (1) goldens produced by the unmodified reference (tests/golden/goldens.json),
+  (2) the reference library itself on identical inputs, operator by operator (oracle/_ref, prebuilt), and
+  (3) the plain-C oracle restatement.
+Contract (BASELINE.json north_star): per-cycle residual norms within 1e-10 relative, error norm and
+order within 1e-6, index mapping bit-exact.  The kernels are built -fmad=false with the reference's
+association order, so the tests demand MORE: bit-for-bit equality (rel tolerance 0)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import hpgmg_b200.api as api
+import oracle_bindings as ob
+
+pytestmark = pytest.mark.gpu
+
+RTOL_NORM = 0.0        # contract: 1e-10; achieved and enforced: exact
+RTOL_ERROR = 0.0       # contract: 1e-6
+
+
+def close(a, b, rtol):
+    return a == b if rtol == 0.0 else abs(a - b) <= rtol * abs(b)
+
+
+# ------------------------------------------------------------------------------------------------ FMG
+GSRB = ["4 1", "5 1", "6 1", "4 8", "5 8", "6 8", "4 27", "5 27", "5 64", "7 8"]
+CHEBY = ["5 1", "5 8", "6 8", "5 27"]
+
+
+@pytest.mark.parametrize("cfg,smoother", [(c, "gsrb") for c in GSRB] + [(c, "cheby") for c in CHEBY])
+def test_fmg_matches_reference_goldens(gpu_lib, cfg, smoother):
+    log2, boxes = map(int, cfg.split())
+    g = ob.goldens()["solves"][f"{cfg} {smoother}"]
+    with api.Hierarchy(log2, boxes, smoother=api.SMOOTHER_CHEBY if smoother == "cheby" else api.SMOOTHER_GSRB) as H:
+        assert [H.level(l).contents.dim.i for l in range(H.num_levels)] == g["dims"]
+        assert [H.level(l).contents.box_dim for l in range(H.num_levels)] == g["box_dims"]
+        eigs = [H.level(l).contents.dominant_eigenvalue_of_DinvA for l in range(H.num_levels)]
+        assert eigs == g["eigs"], "Gershgorin bound per level (rebuild.c:204)"
+        gpu_lib.MGResetTimers(H.mg)
+        err, order, norms = H.richardson()
+        for l in range(3):
+            assert close(norms[l][0], g["norms"][l], RTOL_NORM), f"F-cycle residual norm on level {l}: {norms[l][0]!r} vs {g['norms'][l]!r}"
+        assert norms[0][1] == pytest.approx(g["norms"][0] / g["norm_of_F"], rel=1e-15)
+        assert close(err, g["error"], RTOL_ERROR), (err, g["error"])
+        assert order == pytest.approx(g["order"], rel=1e-12)
+        bottom = H.level(H.num_levels - 1).contents
+        assert bottom.Krylov_iterations == g["krylov_iterations_3_solves"]
+    gpu_lib.hpgmg_b200_set_smoother(api.SMOOTHER_GSRB)
+
+
+def test_graph_replay_equals_stream_launch(gpu_lib):
+    """The captured CUDA graph and plain stream launches run the same kernels: identical bits, and the
+    replay of a recorded graph is deterministic."""
+    out = {}
+    for graphs in (False, True):
+        with api.Hierarchy(5, 8, use_graphs=graphs) as H:
+            a = H.fmg_solve(0)
+            b = H.fmg_solve(0)
+            c = H.fmg_solve(0)
+            assert a == b == c
+            out[graphs] = (a, api.download(H.level(0), 3, api.VECTOR_U).copy())
+    assert out[False][0] == out[True][0]
+    np.testing.assert_array_equal(out[False][1], out[True][1])
+    gpu_lib.hpgmg_b200_use_graphs(1)
+
+
+def test_fmg_solve_host_buffers(gpu_lib):
+    """The end-to-end entry point with HOST buffers (what bench.py's e2e times)."""
+    with api.Hierarchy(5, 8) as H:
+        r, _ = H.fmg_solve(0)
+        Lc = H.level(0).contents
+        vol, nb = Lc.box_volume, Lc.num_my_boxes
+        f = np.concatenate([api.download(H.level(0), b, api.VECTOR_F).reshape(-1) for b in range(nb)])
+        u_ref = np.concatenate([api.download(H.level(0), b, api.VECTOR_U).reshape(-1) for b in range(nb)])
+        u = np.zeros(nb * vol)
+        r2 = gpu_lib.hpgmg_fmg_solve_host(H.mg, 0, api.VECTOR_U, api.VECTOR_F, 0.0, 1.0, 1e-10, f.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p))
+        assert r2 == r
+        np.testing.assert_array_equal(u, u_ref)
+
+
+# ------------------------------------------------------------------------------ operator by operator
+def mirror_random(H, R, rng, levels, ids):
+    """Identical seeded data (ghost zones included) in our device level and the reference's host level."""
+    for l in levels:
+        nb = R.level(l).contents.num_my_boxes
+        for b in range(nb):
+            for vid in ids:
+                a = rng.standard_normal(R.array(l, b, vid).shape)
+                R.array(l, b, vid)[...] = a
+                api.upload(H.level(l), b, vid, a)
+
+
+def assert_level_equal(H, R, l, vid, where, what):
+    Lc = R.level(l).contents
+    n = Lc.box_dim
+    for b in range(Lc.num_my_boxes):
+        ours, ref = api.download(H.level(l), b, vid), R.array(l, b, vid)
+        s = slice(2, 2 + n) if where == "in" else slice(0, n + 4)
+        np.testing.assert_array_equal(ours[s, s, s], ref[s, s, s], err_msg=f"{what}: level {l} box {b} vec {vid} ({where})")
+
+
+OPS = ["exchange_box", "exchange_star", "exchange_nocorners", "bc_v4_box", "bc_v4_nocorners", "bc_v2_box", "bc_v1_box",
+       "apply_op", "residual", "smooth_gsrb", "restrict_cell", "restrict_face_i", "restrict_face_j", "restrict_face_k",
+       "interp_v2", "interp_v4_prescale0", "interp_v4_prescale1", "zero", "init", "scale", "add", "mul", "invert", "shift",
+       "color", "random", "dot_norm_mean", "extrapolate_betas", "rebuild_blackbox", "iterative_solver", "vcycle"]
+
+
+@pytest.mark.skipif(not ob.have_ref(), reason="oracle/_ref (prebuilt reference library) not shipped")
+@pytest.mark.parametrize("cfg", ["4 8", "4 27", "4 1"])
+@pytest.mark.parametrize("op", OPS)
+def test_operator_equals_reference(gpu_lib, cfg, op):
+    log2, boxes = map(int, cfg.split())
+    L = gpu_lib
+    U, E, Rr, T, F, DINV = api.VECTOR_U, api.VECTOR_E, api.VECTOR_R, api.VECTOR_TEMP, api.VECTOR_F, api.VECTOR_DINV
+    BI, BJ, BK = api.VECTOR_BETA_I, api.VECTOR_BETA_J, api.VECTOR_BETA_K
+    with api.Hierarchy(log2, boxes, use_graphs=False) as H:
+        R = ob.RefHierarchy(log2, boxes)
+        rng = np.random.default_rng(hash((cfg, op)) % (2 ** 32))
+        mirror_random(H, R, rng, (0, 1), (U, E, Rr, T))
+        l0, l1, r0, r1 = H.level(0), H.level(1), R.level(0), R.level(1)
+        a, b = 0.0, 1.0
+        checks = []
+
+        def both(name, ours_args, ref_args=None):
+            getattr(L, name)(*ours_args)
+            return R.call(name, *(ref_args if ref_args is not None else [x if not isinstance(x, type(l0)) else x for x in ours_args]))
+
+        if op.startswith("exchange_"):
+            shape = {"box": 0, "star": 1, "nocorners": 2}[op.split("_")[1]]
+            L.exchange_boundary(l0, U, shape); R.call("exchange_boundary", r0, U, shape); checks = [(0, U, "all")]
+        elif op.startswith("bc_"):
+            v, shp = op.split("_")[1], {"box": 0, "nocorners": 2}[op.split("_")[2]]
+            L.exchange_boundary(l0, U, shp); R.call("exchange_boundary", r0, U, shp)
+            getattr(L, f"apply_BCs_{v}")(l0, U, shp); R.call(f"apply_BCs_{v}", r0, U, shp); checks = [(0, U, "all")]
+        elif op == "apply_op":
+            L.apply_op(l0, T, U, a, b); R.call("apply_op", r0, T, U, a, b); checks = [(0, T, "in"), (0, U, "all")]
+        elif op == "residual":
+            L.residual(l0, T, U, Rr, a, b); R.call("residual", r0, T, U, Rr, a, b); checks = [(0, T, "in"), (0, U, "all")]
+        elif op == "smooth_gsrb":
+            L.smooth(l0, U, Rr, a, b); R.call("smooth", r0, U, Rr, a, b); checks = [(0, U, "in"), (0, T, "in")]
+        elif op.startswith("restrict_"):
+            t = {"cell": 0, "face_i": 1, "face_j": 2, "face_k": 3}[op[len("restrict_"):]]
+            L.restriction(l1, Rr, l0, T, t); R.call("restriction", r1, Rr, r0, T, t); checks = [(1, Rr, "all")]
+        elif op == "interp_v2":
+            L.interpolation_v2(l0, U, 1.0, l1, E); R.call("interpolation_v2", r0, U, 1.0, r1, E); checks = [(0, U, "in"), (1, E, "all")]
+        elif op.startswith("interp_v4"):
+            ps = float(op[-1])
+            L.interpolation_v4(l0, U, ps, l1, E); R.call("interpolation_v4", r0, U, ps, r1, E); checks = [(0, U, "in"), (1, E, "all")]
+        elif op == "zero":
+            L.zero_vector(l0, U); R.call("zero_vector", r0, U); checks = [(0, U, "all")]
+        elif op == "init":
+            L.init_vector(l0, U, 3.25); R.call("init_vector", r0, U, 3.25); checks = [(0, U, "all")]
+        elif op == "scale":
+            L.scale_vector(l0, T, -1.7, U); R.call("scale_vector", r0, T, -1.7, U); checks = [(0, T, "all")]
+        elif op == "add":
+            L.add_vectors(l0, T, 0.3, U, -2.1, E); R.call("add_vectors", r0, T, 0.3, U, -2.1, E); checks = [(0, T, "all")]
+        elif op == "mul":
+            L.mul_vectors(l0, T, 1.3, U, E); R.call("mul_vectors", r0, T, 1.3, U, E); checks = [(0, T, "all")]
+        elif op == "invert":
+            L.invert_vector(l0, T, 2.0, U); R.call("invert_vector", r0, T, 2.0, U); checks = [(0, T, "all")]
+        elif op == "shift":
+            L.shift_vector(l0, T, U, 0.125); R.call("shift_vector", r0, T, U, 0.125); checks = [(0, T, "all")]
+        elif op == "color":
+            L.color_vector(l0, T, 4, 1, 2, 3); R.call("color_vector", r0, T, 4, 1, 2, 3); checks = [(0, T, "all")]
+        elif op == "random":
+            L.random_vector(l0, T); R.call("random_vector", r0, T); checks = [(0, T, "all")]
+        elif op == "dot_norm_mean":
+            # the reference's OpenMP reduction order over tiles is only defined for one thread; norm is order-free
+            assert L.norm(l0, U) == R.call("norm", r0, U)
+            import os
+            if R.level(0).contents.num_my_blocks == 1 or os.environ.get("OMP_NUM_THREADS") == "1":
+                assert L.dot(l0, U, E) == R.call("dot", r0, U, E)
+                assert L.mean(l0, U) == R.call("mean", r0, U)
+            else:
+                assert L.dot(l0, U, E) == pytest.approx(R.call("dot", r0, U, E), rel=1e-12)
+                assert L.mean(l0, U) == pytest.approx(R.call("mean", r0, U), rel=1e-10, abs=1e-14)
+            assert L.error(l0, U, E) == R.call("error", r0, U, E)
+        elif op == "extrapolate_betas":
+            mirror_random(H, R, rng, (0,), (BI, BJ, BK))
+            L.extrapolate_betas(l0); R.call("extrapolate_betas", r0)
+            Lc = R.level(0).contents
+            n = Lc.box_dim
+            ring = slice(1, n + 3)       # only the first ghost layer is ever read (and is order-independent)
+            for bx in range(Lc.num_my_boxes):
+                for vid in (BI, BJ, BK):
+                    np.testing.assert_array_equal(api.download(l0, bx, vid)[ring, ring, ring], R.array(0, bx, vid)[ring, ring, ring])
+        elif op == "rebuild_blackbox":
+            L.rebuild_operator_blackbox(l0, a, b, 4); R.call("rebuild_operator_blackbox", r0, a, b, 4)
+            assert l0.contents.dominant_eigenvalue_of_DinvA == r0.contents.dominant_eigenvalue_of_DinvA
+            checks = [(0, DINV, "in"), (0, E, "in")]
+        elif op == "iterative_solver":
+            lb, rb = H.level(H.num_levels - 1), R.level(R.num_levels - 1)
+            mirror_random(H, R, rng, (H.num_levels - 1,), (U, Rr))
+            L.IterativeSolver(lb, U, Rr, a, b, 1e-3); R.call("IterativeSolver", rb, U, Rr, a, b, 1e-3)
+            checks = [(H.num_levels - 1, U, "in")]
+        elif op == "vcycle":
+            L.MGVCycle(H.mg, E, Rr, a, b, 0); R.call("MGVCycle", R.mg, E, Rr, a, b, 0)
+            checks = [(l, E, "in") for l in range(H.num_levels)]
+        else:
+            raise AssertionError(op)
+        for l, vid, where in checks:
+            assert_level_equal(H, R, l, vid, where, op)
+
+
+@pytest.mark.skipif(not ob.have_ref(True), reason="oracle/_ref (prebuilt Chebyshev reference library) not shipped")
+def test_chebyshev_smoother_equals_reference(gpu_lib):
+    with api.Hierarchy(4, 8, smoother=api.SMOOTHER_CHEBY, use_graphs=False) as H:
+        R = ob.RefHierarchy(4, 8, cheby=True)
+        rng = np.random.default_rng(7)
+        mirror_random(H, R, rng, (0,), (api.VECTOR_U, api.VECTOR_R, api.VECTOR_TEMP))
+        assert H.level(0).contents.dominant_eigenvalue_of_DinvA == R.level(0).contents.dominant_eigenvalue_of_DinvA
+        gpu_lib.smooth(H.level(0), api.VECTOR_U, api.VECTOR_R, 0.0, 1.0)
+        R.call("smooth", R.level(0), api.VECTOR_U, api.VECTOR_R, 0.0, 1.0)
+        assert_level_equal(H, R, 0, api.VECTOR_U, "in", "chebyshev")
+        assert_level_equal(H, R, 0, api.VECTOR_TEMP, "in", "chebyshev")
+    gpu_lib.hpgmg_b200_set_smoother(api.SMOOTHER_GSRB)
+
+
+# ------------------------------------------------------------------------------ against the C oracle
+def test_setup_and_solution_equal_oracle_cell_by_cell(gpu_lib):
+    """One 32^3 box: Dinv, betas (with first ghost layer), and U/R of every level after an F-cycle."""
+    O = ob.oracle()
+    Ho = O.oracle_build(5, 0)
+    nF = C.c_double()
+    r_or = O.oracle_fmg_solve(Ho, 0, C.byref(nF))
+    with api.Hierarchy(5, 1) as H:
+        r, rel = H.fmg_solve(0)
+        assert r == r_or and rel == pytest.approx(r_or / nF.value, rel=1e-15)
+        for l in range(H.num_levels):
+            n = H.level(l).contents.box_dim
+            inner, ring = slice(2, 2 + n), slice(1, 3 + n)
+            for vid in (api.VECTOR_DINV, api.VECTOR_U, api.VECTOR_R):
+                np.testing.assert_array_equal(api.download(H.level(l), 0, vid)[inner, inner, inner], ob.oracle_array(Ho, l, vid)[inner, inner, inner])
+            for vid in (api.VECTOR_BETA_I, api.VECTOR_BETA_J, api.VECTOR_BETA_K):
+                np.testing.assert_array_equal(api.download(H.level(l), 0, vid)[ring, ring, ring], ob.oracle_array(Ho, l, vid)[ring, ring, ring])
+    O.oracle_destroy(Ho)
+
+
+# ------------------------------------------------------------------- size-independent properties, 7 8
+@pytest.fixture(scope="module")
+def big(gpu_lib):
+    H = api.Hierarchy(7, 8)
+    yield H
+    H.close()
+
+
+def test_full_size_goldens_and_determinism(gpu_lib, big):
+    g = ob.goldens()["solves"]["7 8 gsrb"]
+    a = big.fmg_solve(0)
+    b = big.fmg_solve(0)
+    assert a == b
+    assert a[0] == g["norms"][0] == 5.144230117437587e-07
+    # the printed residual really is ||f - A u|| of the returned u
+    gpu_lib.residual(big.level(0), api.VECTOR_TEMP, api.VECTOR_U, api.VECTOR_F, 0.0, 1.0)
+    assert gpu_lib.norm(big.level(0), api.VECTOR_TEMP) == a[0]
+
+
+def test_full_size_zero_rhs_gives_zero_solution(gpu_lib, big):
+    lvl = big.level(0)
+    gpu_lib.scale_vector(lvl, api.VECTOR_E, 1.0, api.VECTOR_F)            # park F
+    gpu_lib.zero_vector(lvl, api.VECTOR_F)
+    gpu_lib.zero_vector(lvl, api.VECTOR_U)
+    gpu_lib.hpgmg_b200_use_graphs(0)
+    gpu_lib.FMGSolve(big.mg, 0, api.VECTOR_U, api.VECTOR_F, 0.0, 1.0, 1e-10)
+    gpu_lib.hpgmg_b200_use_graphs(1)
+    assert gpu_lib.norm(lvl, api.VECTOR_U) == 0.0
+    gpu_lib.scale_vector(lvl, api.VECTOR_F, 1.0, api.VECTOR_E)
+    gpu_lib.exchange_boundary(lvl, api.VECTOR_F, 0)
+
+
+def test_full_size_ghost_fill_is_idempotent_and_linear(gpu_lib, big):
+    lvl = big.level(0)
+    big.fmg_solve(0)
+    gpu_lib.exchange_boundary(lvl, api.VECTOR_U, 2); gpu_lib.apply_BCs(lvl, api.VECTOR_U, 2)
+    first = api.download(lvl, 5, api.VECTOR_U).copy()
+    gpu_lib.exchange_boundary(lvl, api.VECTOR_U, 2); gpu_lib.apply_BCs(lvl, api.VECTOR_U, 2)
+    np.testing.assert_array_equal(first, api.download(lvl, 5, api.VECTOR_U))
+    # homogeneous BCs and the operator are linear: A(2u) == 2 A(u) exactly (power-of-two scaling)
+    gpu_lib.apply_op(lvl, api.VECTOR_TEMP, api.VECTOR_U, 0.0, 1.0)
+    Au = api.download(lvl, 2, api.VECTOR_TEMP).copy()
+    gpu_lib.scale_vector(lvl, api.VECTOR_E, 2.0, api.VECTOR_U)
+    gpu_lib.apply_op(lvl, api.VECTOR_TEMP, api.VECTOR_E, 0.0, 1.0)
+    n = lvl.contents.box_dim
+    s = slice(2, 2 + n)
+    np.testing.assert_array_equal(2.0 * Au[s, s, s], api.download(lvl, 2, api.VECTOR_TEMP)[s, s, s])
+    assert gpu_lib.norm(lvl, api.VECTOR_E) == 2.0 * gpu_lib.norm(lvl, api.VECTOR_U)
+
+
+def test_full_size_restriction_preserves_constants_and_means(gpu_lib, big):
+    l0, l1 = big.level(0), big.level(1)
+    gpu_lib.init_vector(l0, api.VECTOR_E, 1.5)
+    gpu_lib.restriction(l1, api.VECTOR_E, l0, api.VECTOR_E, api.RESTRICT_CELL)
+    n = l1.contents.box_dim
+    s = slice(2, 2 + n)
+    for b in range(l1.contents.num_my_boxes):
+        assert np.all(api.download(l1, b, api.VECTOR_E)[s, s, s] == 1.5)
+    # cell-averaged restriction conserves the mean (up to summation rounding)
+    gpu_lib.restriction(l1, api.VECTOR_E, l0, api.VECTOR_F, api.RESTRICT_CELL)
+    assert gpu_lib.mean(l1, api.VECTOR_E) == pytest.approx(gpu_lib.mean(l0, api.VECTOR_F), rel=1e-9, abs=1e-16)
