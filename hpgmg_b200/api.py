@@ -107,7 +107,7 @@ def lib():
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `make -C hpgmg_b200/csrc` (or __graft_entry__.build()). "
                 "hpgmg_b200 has no CPU fallback.")
-        _lib = bind(C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL))
+        _lib = bind(C.CDLL(LIB_PATH))
     return _lib
 
 

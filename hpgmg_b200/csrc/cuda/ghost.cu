@@ -71,27 +71,29 @@ __global__ void __launch_bounds__(128) bc_v2_kernel(const DLevel L, const int id
   bc_v2_block(L, id, B, threadIdx.x, blockDim.x);
 }
 
-/* linear: every ghost cell of the block mirrors (with sign) the cell one step along the inverted
- * normal (boundary_fv.c:6-90) */
-__global__ void __launch_bounds__(128) bc_v1_kernel(const DLevel L, const int id, const blockCopy_type *__restrict__ blocks)
+/* linear: every ghost cell of a block mirrors (with sign) the cell one step along the inverted
+ * normal (boundary_fv.c:6-90).  With two ghost layers a deeper ghost reads a shallower one, possibly
+ * of ANOTHER block, so the result depends on the order: the whole list is walked by one thread in
+ * list order with k,j,i ascending inside a block -- the reference run on one thread.  The path only
+ * exists for box_dim<2, which the radius-2 fv4 stencil never produces; kept for API completeness. */
+__global__ void bc_v1_kernel(const DLevel L, const int id, const blockCopy_type *__restrict__ blocks, const int nblocks)
 {
-  const blockCopy_type B = blocks[blockIdx.x];
-  const BCGeom G = bc_geometry(B, B.subtype, L.dim, L.jStride, L.kStride);
-  double *__restrict__ x = L.vec(B.read.box, id);
-  int m = 0;
-#pragma unroll
-  for (int a = 0; a < 3; a++) m += G.normal[a] ? 1 : 0;
-  const double scale = (m == 2) ? 1.0 : -1.0;           /* faces -1, edges +1, corners -1 */
-  const int stride = -G.normal[0] - G.normal[1] * L.jStride - G.normal[2] * L.kStride;
-  const int cells = G.ext[0] * G.ext[1] * G.ext[2];
-  /* sequential inside the block like the reference (a deeper ghost reads the shallower one);
-   * these blocks only exist for box_dim<2, i.e. a handful of cells */
-  if (threadIdx.x == 0)
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  for (int e = 0; e < nblocks; e++) {
+    const blockCopy_type B = blocks[e];
+    const BCGeom G = bc_geometry(B, B.subtype, L.dim, L.jStride, L.kStride);
+    double *x = L.vec(B.read.box, id);
+    int m = 0;
+    for (int a = 0; a < 3; a++) m += G.normal[a] ? 1 : 0;
+    const double scale = (m == 2) ? 1.0 : -1.0;           /* faces -1, edges +1, corners -1 */
+    const int stride = -G.normal[0] - G.normal[1] * L.jStride - G.normal[2] * L.kStride;
+    const int cells = G.ext[0] * G.ext[1] * G.ext[2];
     for (int c = 0; c < cells; c++) {
       const int i = c % G.ext[0], j = (c / G.ext[0]) % G.ext[1], k = c / (G.ext[0] * G.ext[1]);
       const int ijk = (i + G.lo[0]) + (j + G.lo[1]) * L.jStride + (k + G.lo[2]) * L.kStride;
       x[ijk] = scale * x[ijk + stride];
     }
+  }
 }
 
 extern "C" void apply_BCs_v1(level_type *level, int x_id, int shape)
@@ -99,7 +101,7 @@ extern "C" void apply_BCs_v1(level_type *level, int x_id, int shape)
   if (shape >= STENCIL_MAX_SHAPES) shape = STENCIL_SHAPE_BOX;
   if (level->boundary_condition.type == BC_PERIODIC) return;
   const DList &list = level->dev->bc[shape];
-  if (list.n > 0) LAUNCH(bc_v1_kernel, list.n, 128, 0, dl_of(level), x_id, list.blocks);
+  if (list.n > 0) LAUNCH(bc_v1_kernel, 1, 32, 0, dl_of(level), x_id, list.blocks, list.n);
 }
 
 extern "C" void apply_BCs_v2(level_type *level, int x_id, int shape)

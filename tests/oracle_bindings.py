@@ -103,6 +103,20 @@ def ref(cheby=False):
 
 
 @contextlib.contextmanager
+def ref_threads(n):
+    """Run the reference on n OpenMP threads (its sums over tiles and its two-layer linear BCs are only
+    order-defined on one thread)."""
+    gomp = C.CDLL("libgomp.so.1")
+    gomp.omp_get_max_threads.restype = C.c_int
+    before = gomp.omp_get_max_threads()
+    gomp.omp_set_num_threads(int(n))
+    try:
+        yield
+    finally:
+        gomp.omp_set_num_threads(before)
+
+
+@contextlib.contextmanager
 def quiet():
     """The reference printf()s its progress: park fd 1 on /dev/null while it runs."""
     sys.stdout.flush()
