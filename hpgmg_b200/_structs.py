@@ -2,8 +2,7 @@
 
 The layouts equal the reference's no-MPI build (finite-volume/source/level.h:65-200, mg.h:22-33), so the
 same classes describe a level built by libhpgmg_b200.so (vectors are DEVICE pointers) and one built by
-the reference itself compiled as a host library by the test suite (vectors are host pointers); only the trailing ``dev`` field is
-ours.  Used by the host layer (api.py) and by the tests to diff block lists entry by entry.
+the reference itself compiled as a host library by the test suite (vectors are host pointers); ``fluxes`` carries our opaque device handle.  Used by the host layer (api.py) and by the tests to diff block lists entry by entry.
 """
 import ctypes as C
 
@@ -82,13 +81,11 @@ class level_type(C.Structure):
                 ("RedBlack_base", C.c_void_p), ("RedBlack_FP", C.c_void_p), ("fluxes", C.c_void_p),
                 ("num_threads", C.c_int), ("timers", _Timers),
                 ("Krylov_iterations", C.c_int), ("CAKrylov_formations_of_G", C.c_int),
-                ("vcycles_from_this_level", C.c_int),
-                ("dev", C.c_void_p),               # B200 extension tail (absent in the reference struct)
-                ("_slack", C.c_char * 64)]         # room so a reference build can never overrun the buffer
+                ("vcycles_from_this_level", C.c_int)]
 
 
 REFERENCE_SIZEOF_LEVEL = 1296                       # no-MPI reference build, measured
-assert level_type.dev.offset == REFERENCE_SIZEOF_LEVEL, level_type.dev.offset
+assert C.sizeof(level_type) == REFERENCE_SIZEOF_LEVEL, C.sizeof(level_type)
 
 
 class _MGTimers(C.Structure):

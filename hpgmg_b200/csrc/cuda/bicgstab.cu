@@ -213,7 +213,7 @@ extern "C" int hpgmg_bicgstab_device(level_type *level, int x_id, int R_id, doub
   if (level->num_my_boxes != 1) return 0;
   if (level->boxes_in.i != 1 || level->boxes_in.j != 1 || level->boxes_in.k != 1) return 0;
   if (level->box_dim > BOTTOM_MAX_DIM || level->box_dim < 2) return 0;
-  hpgmg_device_level *D = level->dev;
+  hpgmg_device_level *D = HPGMG_DEV(level);
   BottomArgs A;
   A.L = D->L;
   A.bc = D->bc[STENCIL_SHAPE_NO_CORNERS].blocks;

@@ -62,7 +62,7 @@ static void launch_blas1(level_type *level, BlasArgs &A)
   const DLevel &L = dl_of(level);
   if (L.nboxes == 0) return;
   A.L = L;
-  A.low = level->dev->low;
+  A.low = HPGMG_DEV(level)->low;
   const int g = (OP == B_ZERO || OP == B_INIT) ? L.ghosts : 0;
   const int n = L.dim + 2 * g;
   const int cells = n * n * n;
@@ -172,7 +172,7 @@ static double ordered_sum(level_type *level, int id_a, int id_b, int mode)
 {
   const int slot = HPGMG_SLOT_SCRATCH + 2;
   double *s = hpgmg_rt_scalar_slots() + slot;
-  hpgmg_device_level *D = level->dev;
+  hpgmg_device_level *D = HPGMG_DEV(level);
   CUDA_CHECK(cudaMemsetAsync(s, 0, sizeof(double), g_stream));
   if (D->ntiles > 0) {
     LAUNCH(tile_sum_kernel, (D->ntiles + 63) / 64, 64, 0, D->L, id_a, id_b, D->tiles, D->ntiles, D->tile_partials, mode);

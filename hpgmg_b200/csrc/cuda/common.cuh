@@ -67,7 +67,7 @@ struct hpgmg_device_level {
   int     ntiles;
 };
 
-static inline const DLevel &dl_of(const level_type *level) { return level->dev->L; }
+static inline const DLevel &dl_of(const level_type *level) { return HPGMG_DEV(level)->L; }
 
 /* max over non-negative doubles through their bit pattern (IEEE order == unsigned integer order) */
 __device__ __forceinline__ void atomic_max_nonneg(double *addr, double v)

@@ -26,7 +26,7 @@ static void free_list(DList *l)
 
 extern "C" void hpgmg_device_level_rebind_vectors(level_type *level)
 {
-  hpgmg_device_level *D = level->dev;
+  hpgmg_device_level *D = HPGMG_DEV(level);
   DLevel &L = D->L;
   L.nboxes = level->num_my_boxes;
   L.nvec = level->numVectors;
@@ -42,7 +42,7 @@ extern "C" void hpgmg_device_level_rebind_vectors(level_type *level)
 extern "C" void hpgmg_device_level_create(level_type *level)
 {
   hpgmg_device_level *D = (hpgmg_device_level *)calloc(1, sizeof(hpgmg_device_level));
-  level->dev = D;
+  HPGMG_SET_DEV(level, D);
   hpgmg_device_level_rebind_vectors(level);
 
   if (hpgmg_rt_layout_only()) return;
@@ -75,7 +75,7 @@ extern "C" void hpgmg_device_level_create(level_type *level)
 
 extern "C" void hpgmg_device_level_upload_transfer_lists(level_type *level)
 {
-  hpgmg_device_level *D = level->dev;
+  hpgmg_device_level *D = HPGMG_DEV(level);
   for (int t = 0; t < 4; t++)
     for (int p = 0; p < 3; p++)
       upload_list(&D->restriction[t][p], level->restriction[t].blocks[p], level->restriction[t].num_blocks[p]);
@@ -85,9 +85,9 @@ extern "C" void hpgmg_device_level_upload_transfer_lists(level_type *level)
 
 extern "C" void hpgmg_device_level_destroy(level_type *level)
 {
-  hpgmg_device_level *D = level->dev;
+  hpgmg_device_level *D = HPGMG_DEV(level);
   if (!D) return;
-  if (hpgmg_rt_layout_only()) { free(D); level->dev = NULL; return; }
+  if (hpgmg_rt_layout_only()) { free(D); HPGMG_SET_DEV(level, NULL); return; }
   CUDA_CHECK(cudaStreamSynchronize(g_stream));
   for (int s = 0; s < STENCIL_MAX_SHAPES; s++) {
     free_list(&D->bc[s]);
@@ -99,5 +99,5 @@ extern "C" void hpgmg_device_level_destroy(level_type *level)
   if (D->tiles) CUDA_CHECK(cudaFree(D->tiles));
   if (D->tile_partials) CUDA_CHECK(cudaFree(D->tile_partials));
   free(D);
-  level->dev = NULL;
+  HPGMG_SET_DEV(level, NULL);
 }

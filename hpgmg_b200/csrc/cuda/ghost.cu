@@ -45,7 +45,7 @@ void hpgmg_run_copy_list(const DLevel &L, int id, const DList &list)
 extern "C" void exchange_boundary(level_type *level, int id, int shape)
 {
   if (shape >= STENCIL_MAX_SHAPES) shape = STENCIL_SHAPE_BOX;
-  hpgmg_device_level *D = level->dev;
+  hpgmg_device_level *D = HPGMG_DEV(level);
   if (level->num_ranks > 1 && (level->exchange_ghosts[shape].num_sends > 0 || level->exchange_ghosts[shape].num_recvs > 0)) {
     hpgmg_run_copy_list(D->L, id, D->exchange[shape][0]);                 /* pack   */
     hpgmg_comm_exchange(level, &level->exchange_ghosts[shape], 0);         /* send / recv */
@@ -100,7 +100,7 @@ extern "C" void apply_BCs_v1(level_type *level, int x_id, int shape)
 {
   if (shape >= STENCIL_MAX_SHAPES) shape = STENCIL_SHAPE_BOX;
   if (level->boundary_condition.type == BC_PERIODIC) return;
-  const DList &list = level->dev->bc[shape];
+  const DList &list = HPGMG_DEV(level)->bc[shape];
   if (list.n > 0) LAUNCH(bc_v1_kernel, 1, 32, 0, dl_of(level), x_id, list.blocks, list.n);
 }
 
@@ -109,7 +109,7 @@ extern "C" void apply_BCs_v2(level_type *level, int x_id, int shape)
   if (shape >= STENCIL_MAX_SHAPES) shape = STENCIL_SHAPE_BOX;
   if (level->boundary_condition.type == BC_PERIODIC) return;
   if (level->box_dim < 2) { apply_BCs_v1(level, x_id, shape); return; }
-  const DList &list = level->dev->bc[shape];
+  const DList &list = HPGMG_DEV(level)->bc[shape];
   if (list.n > 0) LAUNCH(bc_v2_kernel, list.n, 128, 0, dl_of(level), x_id, list.blocks);
 }
 
@@ -119,7 +119,7 @@ extern "C" void apply_BCs_v4(level_type *level, int x_id, int shape)
   if (level->boundary_condition.type == BC_PERIODIC) return;
   if (level->box_ghosts < 2) { fprintf(stderr, "called quartic BC's with only 1 ghost zone!!!\n"); exit(0); }
   if (level->box_dim < 4) { apply_BCs_v2(level, x_id, shape); return; }
-  const DList &list = level->dev->bc[shape];
+  const DList &list = HPGMG_DEV(level)->bc[shape];
   if (list.n > 0) LAUNCH(bc_v4_kernel, list.n, 128, 0, dl_of(level), x_id, list.blocks);
 }
 
@@ -179,6 +179,6 @@ __global__ void extrapolate_betas_kernel(const DLevel L, const blockCopy_type *_
 extern "C" void extrapolate_betas(level_type *level)
 {
   if (level->boundary_condition.type == BC_PERIODIC) return;
-  const DList &list = level->dev->bc[STENCIL_SHAPE_BOX];
+  const DList &list = HPGMG_DEV(level)->bc[STENCIL_SHAPE_BOX];
   if (list.n > 0) LAUNCH(extrapolate_betas_kernel, (list.n + 63) / 64, 64, 0, dl_of(level), list.blocks, list.n);
 }

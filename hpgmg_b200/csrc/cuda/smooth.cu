@@ -82,7 +82,7 @@ static void launch_stencil(level_type *level, StencilArgs &A)
   const DLevel &L = dl_of(level);
   if (L.nboxes == 0) return;
   A.L = L;
-  A.low = level->dev->low;
+  A.low = HPGMG_DEV(level)->low;
   A.h2inv = 1.0 / (level->h * level->h);
   const int n = L.dim;
   dim3 block(n >= 32 ? 32 : (n >= 16 ? 16 : 8), n >= 32 ? 4 : 4, n >= 32 ? 2 : 4);
@@ -229,7 +229,7 @@ extern "C" void rebuild_operator_blackbox(level_type *level, double a, double b,
   if (L.nboxes > 0) {
     const int cells = L.dim * L.dim * L.dim;
     dim3 grid((cells + 255) / 256 > 1024 ? 1024 : (cells + 255) / 256, L.nboxes);
-    LAUNCH(rebuild_finish_kernel, grid, 256, 0, L, level->dev->low, Aii_id, sum_id, a, b, 1.0 / (level->h * level->h), slot);
+    LAUNCH(rebuild_finish_kernel, grid, 256, 0, L, HPGMG_DEV(level)->low, Aii_id, sum_id, a, b, 1.0 / (level->h * level->h), slot);
   }
   double eig = 0.0;
   hpgmg_rt_read_scalars(&eig, HPGMG_SLOT_SCRATCH, 1);

@@ -459,7 +459,7 @@ void create_vectors(level_type *L, int numVectors)
     box->global_box_id = id;
   }
   L->numVectors = numVectors;
-  if (L->dev) hpgmg_device_level_rebind_vectors(L);
+  if (HPGMG_DEV(L)) hpgmg_device_level_rebind_vectors(L);
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -10,6 +10,14 @@
 #include <stddef.h>
 #include "hpgmg_b200.h"
 
+/* The device mirror of a level (lists, slab geometry) hangs off level_type::fluxes -- a pointer the
+ * reference only uses in its experimental flux smoother (level.h, `fluxes`) -- so that level_type
+ * keeps EXACTLY the reference's size and layout and a caller compiled against the reference's own
+ * level.h can hand us its struct. */
+struct hpgmg_device_level;
+#define HPGMG_DEV(level)        ((struct hpgmg_device_level *)(level)->fluxes)
+#define HPGMG_SET_DEV(level, p) ((level)->fluxes = (double *)(p))
+
 #ifdef __cplusplus
 extern "C" {
 #endif

@@ -4,15 +4,15 @@
  * This is the drop-in boundary for the reference's level.h
  * (/root/reference/finite-volume/source/level.h:65-215): same type names, same field names,
  * same field order and the same sizes for the no-MPI build (blockCopy_type 128 B,
- * communicator_type 104 B, box_type 56 B, level_type 1296 B up to the extension tail), so a
+ * communicator_type 104 B, box_type 56 B, level_type 1296 B), so a
  * caller written against the reference header compiles and links unchanged.
  *
  * What differs is where the bytes live:
  *   - box_type.vectors[id] and every communicator buffer are DEVICE pointers (HBM of the GPU
  *     this rank owns).  Host code may do pointer arithmetic on them but must never
  *     dereference them; use hpgmg_b200.h (hpgmg_download_box_vector & co) to move data.
- *   - level_type gains a trailing `dev` pointer to the device-side mirror of the block lists.
- *     Reference callers only use named fields, so the tail is invisible to them.
+ *   - level_type::fluxes (unused by the reference's default build) carries an opaque handle to the
+ *     device-side mirror of the block lists, so the struct is byte-for-byte the reference's.
  */
 #ifndef HPGMG_B200_LEVEL_H
 #define HPGMG_B200_LEVEL_H
@@ -96,8 +96,6 @@ typedef struct {
   double  *fp_base;                              /* DEVICE base of this box's 4-D array    */
 } box_type;
 
-struct hpgmg_device_level;                       /* opaque: device mirror (csrc/cuda)      */
-
 /* One multigrid level. -- level.h:112-200 */
 typedef struct {
   double h;                                      /* grid spacing                           */
@@ -135,7 +133,8 @@ typedef struct {
   int    must_subtract_mean;
   double *RedBlack_base;                         /* kept for layout parity; unused on GPU  */
   double *RedBlack_FP;
-  double *fluxes;
+  double *fluxes;                                /* reference: scratch of the experimental flux smoother;
+                                                    here: opaque handle of the device mirror (lists, geometry) */
 
   int num_threads;
 
@@ -153,9 +152,6 @@ typedef struct {
   int Krylov_iterations;
   int CAKrylov_formations_of_G;
   int vcycles_from_this_level;
-
-  /* ---- B200 extension tail (not present in the reference struct) ---------------------- */
-  struct hpgmg_device_level *dev;                /* device mirror of lists, stream, scratch */
 } level_type;
 
 /* level.c:1075,1305,929,1265,95,313 */

@@ -293,3 +293,19 @@ def test_full_size_restriction_preserves_constants_and_means(gpu_lib, big):
     # cell-averaged restriction conserves the mean (up to summation rounding)
     gpu_lib.restriction(l1, api.VECTOR_E, l0, api.VECTOR_F, api.RESTRICT_CELL)
     assert gpu_lib.mean(l1, api.VECTOR_E) == pytest.approx(gpu_lib.mean(l0, api.VECTOR_F), rel=1e-9, abs=1e-16)
+
+
+# --------------------------------------------------------------------------------- drop-in, literally
+def test_unmodified_reference_driver_runs_on_our_library(gpu_lib):
+    """hpgmg_b200/bin/hpgmg-fv-refdriver = the reference's own hpgmg-fv.c (compiled with the reference's own
+    headers) linked against libhpgmg_b200.so.  Its printed F-cycle norms / error must be the goldens."""
+    import os, re, subprocess
+    exe = os.path.join(os.path.dirname(api.LIB_PATH), "..", "bin", "hpgmg-fv-refdriver")
+    if not os.path.exists(exe):
+        pytest.skip("hpgmg-fv-refdriver not built (needs /root/reference at build time)")
+    out = subprocess.run([exe, "6", "1"], capture_output=True, text=True, timeout=600).stdout
+    g = ob.goldens()["solves"]["6 1 gsrb"]
+    norms = [float(x) for x in re.findall(r"f-cycle\s+norm=([0-9.e+-]+)", out)]
+    assert norms[-3:] == g["norms"], out[-2000:]
+    assert float(re.search(r"\|\|error\|\|=([0-9.e+-]+)", out).group(1)) == pytest.approx(g["error"], rel=1e-15)
+    assert "DOF/s=" in out
