@@ -76,6 +76,31 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(const StencilArgs 
   }
 }
 
+#include "stencil_tiled.cuh"
+
+static int g_force_generic = -1, g_kchunk_override = -1;
+
+template <int OP, int TI, int TJ>
+static void launch_tiled(const StencilArgs &A)
+{
+  typedef TileCfg<TI, TJ> C;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(stencil_tiled_kernel<OP, TI, TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    configured = true;
+  }
+  const int n = A.L.dim;
+  const int tiles = (n / TI) * (n / TJ);
+  /* split k so that the grid fills the 148 SMs x 2 resident blocks, but keep chunks >= 16 planes
+   * (each chunk re-reads a 4-plane prologue) */
+  int chunks = 1;
+  while (tiles * A.L.nboxes * chunks < 296 && n / (chunks * 2) >= 16) chunks *= 2;
+  if (g_kchunk_override > 0) chunks = (n + g_kchunk_override - 1) / g_kchunk_override;
+  const int kchunk = (n + chunks - 1) / chunks;
+  dim3 grid(tiles, chunks, A.L.nboxes), block(TI / 2, TJ);
+  LAUNCH((stencil_tiled_kernel<OP, TI, TJ>), grid, block, C::SMEM, A, kchunk);
+}
+
 template <int OP>
 static void launch_stencil(level_type *level, StencilArgs &A)
 {
@@ -85,6 +110,16 @@ static void launch_stencil(level_type *level, StencilArgs &A)
   A.low = HPGMG_DEV(level)->low;
   A.h2inv = 1.0 / (level->h * level->h);
   const int n = L.dim;
+  if (g_force_generic < 0) {
+    const char *e = getenv("HPGMG_B200_GENERIC_STENCIL");
+    g_force_generic = (e && atoi(e)) ? 1 : 0;
+    const char *kc = getenv("HPGMG_B200_KCHUNK");
+    if (kc) g_kchunk_override = atoi(kc);
+  }
+  if (OP != OP_REBUILD && !g_force_generic) {
+    if (n % 64 == 0) { launch_tiled<OP, 64, 8>(A); return; }
+    if (n % 32 == 0) { launch_tiled<OP, 32, 8>(A); return; }
+  }
   dim3 block(n >= 32 ? 32 : (n >= 16 ? 16 : 8), n >= 32 ? 4 : 4, n >= 32 ? 2 : 4);
   const int ktiles = (n + block.z - 1) / block.z;
   dim3 grid((n + block.x - 1) / block.x, (n + block.y - 1) / block.y, ktiles * L.nboxes);

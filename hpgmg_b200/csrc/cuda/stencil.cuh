@@ -11,11 +11,59 @@
  *
  * beta_d[ijk] is the coefficient on the LOW d-face of cell ijk.  25 x-points (axis +-1,+-2 and the
  * 12 in-plane diagonals: ghost faces + edges, never corners), 30 beta-points.
+ *
+ * The arithmetic is written ONCE, over four "loaders" X, BI, BJ, BK that return the value at an
+ * offset (di,dj,dk) from the cell: the global-memory kernels pass pointer loaders, the tiled kernels
+ * pass shared-memory loaders; both therefore produce identical bits.
  */
 #ifndef HPGMG_B200_STENCIL_CUH
 #define HPGMG_B200_STENCIL_CUH
 
 #define STENCIL_TWELFTH (0.0833333333333333333)
+
+template <class XL, class BIL, class BJL, class BKL>
+__device__ __forceinline__ double fv4_apply_op_at(const XL &X, const BIL &BI, const BJL &BJ, const BKL &BK, const double b, const double h2inv)
+{
+  const double xc = X(0, 0, 0);
+  const double xw = X(-1, 0, 0), xe = X(1, 0, 0), xww = X(-2, 0, 0), xee = X(2, 0, 0);
+  const double xs = X(0, -1, 0), xn = X(0, 1, 0), xss = X(0, -2, 0), xnn = X(0, 2, 0);
+  const double xd = X(0, 0, -1), xu = X(0, 0, 1), xdd = X(0, 0, -2), xuu = X(0, 0, 2);
+  const double xwn = X(-1, 1, 0), xws = X(-1, -1, 0), xen = X(1, 1, 0), xes = X(1, -1, 0);
+  const double xwu = X(-1, 0, 1), xwd = X(-1, 0, -1), xeu = X(1, 0, 1), xed = X(1, 0, -1);
+  const double xsu = X(0, -1, 1), xsd = X(0, -1, -1), xnu = X(0, 1, 1), xnd = X(0, 1, -1);
+
+  const double axial =
+      BI(0, 0, 0) * (15.0 * (xw - xc) - (xww - xe))
+    + BI(1, 0, 0) * (15.0 * (xe - xc) - (xee - xw))
+    + BJ(0, 0, 0) * (15.0 * (xs - xc) - (xss - xn))
+    + BJ(0, 1, 0) * (15.0 * (xn - xc) - (xnn - xs))
+    + BK(0, 0, 0) * (15.0 * (xd - xc) - (xdd - xu))
+    + BK(0, 0, 1) * (15.0 * (xu - xc) - (xuu - xd));
+
+  const double mixed =
+      (BI(0, 1, 0) - BI(0, -1, 0)) * (xwn - xn - xws + xs)
+    + (BI(0, 0, 1) - BI(0, 0, -1)) * (xwu - xu - xwd + xd)
+    + (BJ(1, 0, 0) - BJ(-1, 0, 0)) * (xes - xe - xws + xw)
+    + (BJ(0, 0, 1) - BJ(0, 0, -1)) * (xsu - xu - xsd + xd)
+    + (BK(1, 0, 0) - BK(-1, 0, 0)) * (xed - xe - xwd + xw)
+    + (BK(0, 1, 0) - BK(0, -1, 0)) * (xnd - xn - xsd + xs)
+
+    + (BI(1, 1, 0) - BI(1, -1, 0)) * (xen - xn - xes + xs)
+    + (BI(1, 0, 1) - BI(1, 0, -1)) * (xeu - xu - xed + xd)
+    + (BJ(1, 1, 0) - BJ(-1, 1, 0)) * (xen - xe - xwn + xw)
+    + (BJ(0, 1, 1) - BJ(0, 1, -1)) * (xnu - xu - xnd + xd)
+    + (BK(1, 0, 1) - BK(-1, 0, 1)) * (xeu - xe - xwu + xw)
+    + (BK(0, 1, 1) - BK(0, -1, 1)) * (xnu - xn - xsu + xs);
+
+  return -b * h2inv * (STENCIL_TWELFTH * axial + 0.25 * STENCIL_TWELFTH * mixed);
+}
+
+/* loader over a global-memory array: p points at cell ijk */
+struct GlobalLoader {
+  const double *__restrict__ p;
+  int jS, kS;
+  __device__ __forceinline__ double operator()(const int di, const int dj, const int dk) const { return p[di + dj * jS + dk * kS]; }
+};
 
 /* x, bi, bj, bk point at cell ijk; jS/kS are the strides (doubles). Returns A x at ijk. */
 __device__ __forceinline__ double fv4_apply_op(const double *__restrict__ x,
@@ -25,38 +73,8 @@ __device__ __forceinline__ double fv4_apply_op(const double *__restrict__ x,
                                                const int jS, const int kS,
                                                const double b, const double h2inv)
 {
-  const double xc = x[0];
-  const double xw = x[-1],  xe = x[1],   xww = x[-2],      xee = x[2];
-  const double xs = x[-jS], xn = x[jS],  xss = x[-2 * jS], xnn = x[2 * jS];
-  const double xd = x[-kS], xu = x[kS],  xdd = x[-2 * kS], xuu = x[2 * kS];
-  const double xwn = x[-1 + jS], xws = x[-1 - jS], xen = x[1 + jS], xes = x[1 - jS];
-  const double xwu = x[-1 + kS], xwd = x[-1 - kS], xeu = x[1 + kS], xed = x[1 - kS];
-  const double xsu = x[-jS + kS], xsd = x[-jS - kS], xnu = x[jS + kS], xnd = x[jS - kS];
-
-  const double axial =
-      bi[0]  * (15.0 * (xw - xc) - (xww - xe))
-    + bi[1]  * (15.0 * (xe - xc) - (xee - xw))
-    + bj[0]  * (15.0 * (xs - xc) - (xss - xn))
-    + bj[jS] * (15.0 * (xn - xc) - (xnn - xs))
-    + bk[0]  * (15.0 * (xd - xc) - (xdd - xu))
-    + bk[kS] * (15.0 * (xu - xc) - (xuu - xd));
-
-  const double mixed =
-      (bi[jS]     - bi[-jS])     * (xwn - xn - xws + xs)
-    + (bi[kS]     - bi[-kS])     * (xwu - xu - xwd + xd)
-    + (bj[1]      - bj[-1])      * (xes - xe - xws + xw)
-    + (bj[kS]     - bj[-kS])     * (xsu - xu - xsd + xd)
-    + (bk[1]      - bk[-1])      * (xed - xe - xwd + xw)
-    + (bk[jS]     - bk[-jS])     * (xnd - xn - xsd + xs)
-
-    + (bi[1 + jS] - bi[1 - jS])  * (xen - xn - xes + xs)
-    + (bi[1 + kS] - bi[1 - kS])  * (xeu - xu - xed + xd)
-    + (bj[jS + 1] - bj[jS - 1])  * (xen - xe - xwn + xw)
-    + (bj[jS + kS] - bj[jS - kS]) * (xnu - xu - xnd + xd)
-    + (bk[kS + 1] - bk[kS - 1])  * (xeu - xe - xwu + xw)
-    + (bk[kS + jS] - bk[kS - jS]) * (xnu - xn - xsu + xs);
-
-  return -b * h2inv * (STENCIL_TWELFTH * axial + 0.25 * STENCIL_TWELFTH * mixed);
+  const GlobalLoader X = { x, jS, kS }, BI = { bi, jS, kS }, BJ = { bj, jS, kS }, BK = { bk, jS, kS };
+  return fv4_apply_op_at(X, BI, BJ, BK, b, h2inv);
 }
 
 #endif
