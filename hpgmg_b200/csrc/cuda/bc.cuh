@@ -1,13 +1,18 @@
 /*
  * bc.cuh -- device bodies of the homogeneous-Dirichlet ghost-cell extrapolations, shared by the
- * list-walking kernels in ghost.cu and the single-block bottom solver in bicgstab.cu.
- * Reference: operators/boundary_fv.c:101-250 (quadratic), :262-569 (quartic).
+ * list-walking kernels (ghost.cu), the single-block bottom solver (bicgstab.cuh) and the coarse-cycle
+ * kernel (coarse.cu).  Reference: operators/boundary_fv.c:101-250 (quadratic), :262-569 (quartic).
+ *
+ * Unit of work = one COLUMN: one tangential position of a BC region.  Along each axis that is normal
+ * to the domain boundary the column owns the 2 ghost cells and reads the 4 (v4) or 2 (v2) interior
+ * cells behind them.  With M normal axes (1 face, 2 edge, 3 corner) the quartic version gathers 4^M
+ * values and extrapolates axis by axis in ascending axis order -- the order of the reference's
+ * face / 16-point edge (:404-425) / 64-point corner (:507-565) code -- so results are bit-identical.
  */
 #ifndef HPGMG_B200_BC_CUH
 #define HPGMG_B200_BC_CUH
 #include "common.cuh"
 
-/* ---- boundary conditions ----------------------------------------------------------------------- */
 /* 1-D quartic extrapolation of cell averages through a zero Dirichlet face (boundary_fv.c:339-340):
  * x1..x4 are the four cells nearest the boundary; near/far are the first/second ghost cell. */
 __device__ __forceinline__ void quartic_pair(const double x1, const double x2, const double x3, const double x4, double &near, double &far)
@@ -17,16 +22,116 @@ __device__ __forceinline__ void quartic_pair(const double x1, const double x2, c
   far  = OneTwelfth * (-505.0 * x1 + 335.0 * x2 - 145.0 * x3 + 27.0 * x4);
 }
 
-/* geometry of a BC entry: for each axis, is it normal to the domain boundary, where is the nearest
- * ghost cell and which way is inward */
+/* ---- one column, quartic ------------------------------------------------------------------------ */
+/* x points at cell (0,0,0) of the box vector, ijk is the offset of the column's nearest ghost cell,
+ * d0<d1<d2 (axis order) are the inward strides of the normal axes. */
+__device__ __forceinline__ void bc_v4_col1(double *x, const int ijk, const int d0)
+{
+  double n, f;
+  quartic_pair(x[ijk + d0], x[ijk + 2 * d0], x[ijk + 3 * d0], x[ijk + 4 * d0], n, f);
+  x[ijk] = n;
+  x[ijk - d0] = f;
+}
+__device__ __forceinline__ void bc_v4_col2(double *x, const int ijk, const int d0, const int d1)
+{
+  double n[4], f[4];
+#pragma unroll
+  for (int J = 0; J < 4; J++) {
+    const int o = ijk + (J + 1) * d1;
+    quartic_pair(x[o + d0], x[o + 2 * d0], x[o + 3 * d0], x[o + 4 * d0], n[J], f[J]);
+  }
+  double nn, nf, fn, ff;
+  quartic_pair(n[0], n[1], n[2], n[3], nn, nf);
+  quartic_pair(f[0], f[1], f[2], f[3], fn, ff);
+  x[ijk] = nn;
+  x[ijk - d1] = nf;
+  x[ijk - d0] = fn;
+  x[ijk - d0 - d1] = ff;
+}
+__device__ __forceinline__ void bc_v4_col3(double *x, const int ijk, const int d0, const int d1, const int d2)
+{
+  double nn[4], nf[4], fn[4], ff[4];
+#pragma unroll
+  for (int K = 0; K < 4; K++) {
+    double n[4], f[4];
+#pragma unroll
+    for (int J = 0; J < 4; J++) {
+      const int o = ijk + (J + 1) * d1 + (K + 1) * d2;
+      quartic_pair(x[o + d0], x[o + 2 * d0], x[o + 3 * d0], x[o + 4 * d0], n[J], f[J]);
+    }
+    quartic_pair(n[0], n[1], n[2], n[3], nn[K], nf[K]);
+    quartic_pair(f[0], f[1], f[2], f[3], fn[K], ff[K]);
+  }
+  double nnn, nnf, nfn, nff, fnn, fnf, ffn, fff;
+  quartic_pair(nn[0], nn[1], nn[2], nn[3], nnn, nnf);
+  quartic_pair(nf[0], nf[1], nf[2], nf[3], nfn, nff);
+  quartic_pair(fn[0], fn[1], fn[2], fn[3], fnn, fnf);
+  quartic_pair(ff[0], ff[1], ff[2], ff[3], ffn, fff);
+  x[ijk] = nnn;
+  x[ijk - d2] = nnf;
+  x[ijk - d1] = nfn;
+  x[ijk - d1 - d2] = nff;
+  x[ijk - d0] = fnn;
+  x[ijk - d0 - d2] = fnf;
+  x[ijk - d0 - d1] = ffn;
+  x[ijk - d0 - d1 - d2] = fff;
+}
+
+/* ---- one column, quadratic: only the nearest ghost cell (boundary_fv.c:169, :206-209, :238-245) ---- */
+__device__ __forceinline__ void bc_v2_col(double *x, const int ijk, const int m, const int d0, const int d1, const int d2)
+{
+  if (m == 1) {
+    x[ijk] = -2.5 * x[ijk + d0] + 0.5 * x[ijk + 2 * d0];
+  } else if (m == 2) {
+    x[ijk] = 6.25 * x[ijk + d0 + d1]
+           - 1.25 * x[ijk + 2 * d0 + d1]
+           - 1.25 * x[ijk + d0 + 2 * d1]
+           + 0.25 * x[ijk + 2 * d0 + 2 * d1];
+  } else {
+    x[ijk] = -15.625 * x[ijk + d0 + d1 + d2]
+            + 3.125 * x[ijk + 2 * d0 + d1 + d2]
+            + 3.125 * x[ijk + d0 + 2 * d1 + d2]
+            + 3.125 * x[ijk + d0 + d1 + 2 * d2]
+            - 0.625 * x[ijk + 2 * d0 + 2 * d1 + d2]
+            - 0.625 * x[ijk + d0 + 2 * d1 + 2 * d2]
+            - 0.625 * x[ijk + 2 * d0 + d1 + 2 * d2]
+            + 0.125 * x[ijk + 2 * d0 + 2 * d1 + 2 * d2];
+  }
+}
+
+/* the normal axes of a domain normal `subtype` (0..26 = 13+di+3dj+9dk): their count and inward strides */
+struct BCNormal {
+  int m, d[3];
+  int normal[3];
+};
+__device__ __forceinline__ BCNormal bc_normal(const int subtype, const int jS, const int kS)
+{
+  BCNormal N;
+  N.normal[0] = (subtype % 3) - 1;
+  N.normal[1] = ((subtype % 9) / 3) - 1;
+  N.normal[2] = (subtype / 9) - 1;
+  const int stride[3] = { 1, jS, kS };
+  N.m = 0;
+  N.d[0] = N.d[1] = N.d[2] = 0;
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+    if (N.normal[a]) N.d[N.m++] = (N.normal[a] < 0) ? stride[a] : -stride[a];
+  return N;
+}
+__device__ __forceinline__ void bc_v4_column(double *x, const int ijk, const BCNormal &N)
+{
+  if (N.m == 1)      bc_v4_col1(x, ijk, N.d[0]);
+  else if (N.m == 2) bc_v4_col2(x, ijk, N.d[0], N.d[1]);
+  else               bc_v4_col3(x, ijk, N.d[0], N.d[1], N.d[2]);
+}
+
+/* ---- one list entry (a block of columns), cooperatively by nthreads threads ---------------------- */
 struct BCGeom {
   int normal[3];     /* -1 low side, +1 high side, 0 tangential   (domain normal)       */
   int t[3];          /* coordinate of the nearest ghost cell along a normal axis          */
-  int inward[3];     /* +stride or -stride: one cell towards the interior                */
   int stride[3];
   int lo[3], ext[3]; /* block origin and extent                                           */
 };
-
 __device__ __forceinline__ BCGeom bc_geometry(const blockCopy_type &B, const int subtype, const int dim, const int jS, const int kS)
 {
   BCGeom G;
@@ -37,141 +142,56 @@ __device__ __forceinline__ BCGeom bc_geometry(const blockCopy_type &B, const int
   G.lo[0] = B.read.i;  G.lo[1] = B.read.j;  G.lo[2] = B.read.k;
   G.ext[0] = B.dim.i;  G.ext[1] = B.dim.j;  G.ext[2] = B.dim.k;
 #pragma unroll
-  for (int a = 0; a < 3; a++) {
-    G.t[a] = (G.normal[a] < 0) ? -1 : dim;
-    G.inward[a] = (G.normal[a] < 0) ? G.stride[a] : -G.stride[a];
-  }
+  for (int a = 0; a < 3; a++) G.t[a] = (G.normal[a] < 0) ? -1 : dim;
   return G;
 }
+/* number of columns of a block and the offset of column c's nearest ghost cell */
+__device__ __forceinline__ int bc_num_columns(const BCGeom &G)
+{
+  return (G.normal[0] ? 1 : G.ext[0]) * (G.normal[1] ? 1 : G.ext[1]) * (G.normal[2] ? 1 : G.ext[2]);
+}
+__device__ __forceinline__ int bc_column_offset(const BCGeom &G, const int c)
+{
+  const int e0 = G.normal[0] ? 1 : G.ext[0], e1 = G.normal[1] ? 1 : G.ext[1];
+  const int p0 = c % e0, p1 = (c / e0) % e1, p2 = c / (e0 * e1);
+  return (G.normal[0] ? G.t[0] : p0 + G.lo[0]) * G.stride[0]
+       + (G.normal[1] ? G.t[1] : p1 + G.lo[1]) * G.stride[1]
+       + (G.normal[2] ? G.t[2] : p2 + G.lo[2]) * G.stride[2];
+}
+__device__ __forceinline__ void bc_zero_block(double *x, const BCGeom &G, const int tid, const int nthreads)
+{
+  const int cells = G.ext[0] * G.ext[1] * G.ext[2];
+  for (int c = tid; c < cells; c += nthreads) {
+    const int i = c % G.ext[0], j = (c / G.ext[0]) % G.ext[1], k = c / (G.ext[0] * G.ext[1]);
+    x[(i + G.lo[0]) * G.stride[0] + (j + G.lo[1]) * G.stride[1] + (k + G.lo[2]) * G.stride[2]] = 0.0;
+  }
+}
 
-/* one BC list entry, worked on cooperatively by the nthreads threads of a thread block */
 __device__ __forceinline__ void bc_v4_block(const DLevel &L, const int id, const blockCopy_type &B, const int tid, const int nthreads)
 {
   const BCGeom G = bc_geometry(B, B.subtype, L.dim, L.jStride, L.kStride);
-  double *__restrict__ x = L.vec(B.read.box, id);
-
+  const BCNormal N = bc_normal(B.subtype, L.jStride, L.kStride);
+  double *x = L.vec(B.read.box, id);
   if (L.ghosts > 2) {                                    /* boundary_fv.c:299-306 */
-    const int cells = G.ext[0] * G.ext[1] * G.ext[2];
-    for (int c = tid; c < cells; c += nthreads) {
-      const int i = c % G.ext[0], j = (c / G.ext[0]) % G.ext[1], k = c / (G.ext[0] * G.ext[1]);
-      x[(i + G.lo[0]) + (j + G.lo[1]) * L.jStride + (k + G.lo[2]) * L.kStride] = 0.0;
-    }
+    bc_zero_block(x, G, tid, nthreads);
     __syncthreads();
   }
-
-  /* tangential extent (axes that are not normal): one thread per tangential position */
-  int text[3], cols = 1;
-#pragma unroll
-  for (int a = 0; a < 3; a++) { text[a] = G.normal[a] ? 1 : G.ext[a]; cols *= text[a]; }
-
-  for (int c = tid; c < cols; c += nthreads) {
-    int p[3];
-    p[0] = c % text[0];  p[1] = (c / text[0]) % text[1];  p[2] = c / (text[0] * text[1]);
-    int ijk = 0;
-#pragma unroll
-    for (int a = 0; a < 3; a++) ijk += (G.normal[a] ? G.t[a] : (p[a] + G.lo[a])) * G.stride[a];
-
-    /* gather the 4^m interior values: v[I][J][K], index 0..3 <-> 1..4 cells inward */
-    double v[4][4][4];
-    const int ni = G.normal[0] ? 4 : 1, nj = G.normal[1] ? 4 : 1, nk = G.normal[2] ? 4 : 1;
-    for (int K = 0; K < nk; K++)
-    for (int J = 0; J < nj; J++)
-    for (int I = 0; I < ni; I++) {
-      int off = ijk;
-      if (G.normal[0]) off += (I + 1) * G.inward[0];
-      if (G.normal[1]) off += (J + 1) * G.inward[1];
-      if (G.normal[2]) off += (K + 1) * G.inward[2];
-      v[I][J][K] = x[off];
-    }
-    /* extrapolate along i, then j, then k; after a pass the axis holds {near, far} in slots 0,1 */
-    int ci = ni, cj = nj, ck = nk;
-    if (G.normal[0]) {
-      for (int K = 0; K < ck; K++) for (int J = 0; J < cj; J++) {
-        double n, f;
-        quartic_pair(v[0][J][K], v[1][J][K], v[2][J][K], v[3][J][K], n, f);
-        v[0][J][K] = n;  v[1][J][K] = f;
-      }
-      ci = 2;
-    }
-    if (G.normal[1]) {
-      for (int K = 0; K < ck; K++) for (int I = 0; I < ci; I++) {
-        double n, f;
-        quartic_pair(v[I][0][K], v[I][1][K], v[I][2][K], v[I][3][K], n, f);
-        v[I][0][K] = n;  v[I][1][K] = f;
-      }
-      cj = 2;
-    }
-    if (G.normal[2]) {
-      for (int J = 0; J < cj; J++) for (int I = 0; I < ci; I++) {
-        double n, f;
-        quartic_pair(v[I][J][0], v[I][J][1], v[I][J][2], v[I][J][3], n, f);
-        v[I][J][0] = n;  v[I][J][1] = f;
-      }
-      ck = 2;
-    }
-    /* commit: slot 0 = nearest ghost, slot 1 = one further out (away from the interior) */
-    for (int K = 0; K < ck; K++)
-    for (int J = 0; J < cj; J++)
-    for (int I = 0; I < ci; I++) {
-      int off = ijk;
-      if (G.normal[0]) off -= I * G.inward[0];
-      if (G.normal[1]) off -= J * G.inward[1];
-      if (G.normal[2]) off -= K * G.inward[2];
-      x[off] = v[I][J][K];
-    }
-  }
+  const int cols = bc_num_columns(G);
+  for (int c = tid; c < cols; c += nthreads) bc_v4_column(x, bc_column_offset(G, c), N);
 }
 
-/* quadratic: only the first ghost layer is extrapolated, deeper layers are zeroed (boundary_fv.c:101-250) */
+/* quadratic: deeper ghost layers are zeroed first (boundary_fv.c:139-145) */
 __device__ __forceinline__ void bc_v2_block(const DLevel &L, const int id, const blockCopy_type &B, const int tid, const int nthreads)
 {
   const BCGeom G = bc_geometry(B, B.subtype, L.dim, L.jStride, L.kStride);
-  double *__restrict__ x = L.vec(B.read.box, id);
-
+  const BCNormal N = bc_normal(B.subtype, L.jStride, L.kStride);
+  double *x = L.vec(B.read.box, id);
   if (L.ghosts > 1) {
-    const int cells = G.ext[0] * G.ext[1] * G.ext[2];
-    for (int c = tid; c < cells; c += nthreads) {
-      const int i = c % G.ext[0], j = (c / G.ext[0]) % G.ext[1], k = c / (G.ext[0] * G.ext[1]);
-      x[(i + G.lo[0]) + (j + G.lo[1]) * L.jStride + (k + G.lo[2]) * L.kStride] = 0.0;
-    }
+    bc_zero_block(x, G, tid, nthreads);
     __syncthreads();
   }
-  int text[3], cols = 1, m = 0;
-#pragma unroll
-  for (int a = 0; a < 3; a++) { text[a] = G.normal[a] ? 1 : G.ext[a]; cols *= text[a]; m += G.normal[a] ? 1 : 0; }
-  /* the inward strides of the normal axes in ascending axis order: (dt) | (ds,dt) | (di,dj,dk) */
-  int d[3] = { 0, 0, 0 }, nd = 0;
-#pragma unroll
-  for (int a = 0; a < 3; a++) if (G.normal[a]) d[nd++] = G.inward[a];
-
-  for (int c = tid; c < cols; c += nthreads) {
-    int p[3];
-    p[0] = c % text[0];  p[1] = (c / text[0]) % text[1];  p[2] = c / (text[0] * text[1]);
-    int ijk = 0;
-#pragma unroll
-    for (int a = 0; a < 3; a++) ijk += (G.normal[a] ? G.t[a] : (p[a] + G.lo[a])) * G.stride[a];
-    if (m == 1) {
-      const int dt = d[0];
-      x[ijk] = -2.5 * x[ijk + dt] + 0.5 * x[ijk + 2 * dt];
-    } else if (m == 2) {
-      const int ds = d[0], dt = d[1];
-      x[ijk] = 6.25 * x[ijk + ds + dt]
-             - 1.25 * x[ijk + 2 * ds + dt]
-             - 1.25 * x[ijk + ds + 2 * dt]
-             + 0.25 * x[ijk + 2 * ds + 2 * dt];
-    } else {
-      const int di = d[0], dj = d[1], dk = d[2];
-      x[ijk] = -15.625 * x[ijk + di + dj + dk]
-              + 3.125 * x[ijk + 2 * di + dj + dk]
-              + 3.125 * x[ijk + di + 2 * dj + dk]
-              + 3.125 * x[ijk + di + dj + 2 * dk]
-              - 0.625 * x[ijk + 2 * di + 2 * dj + dk]
-              - 0.625 * x[ijk + di + 2 * dj + 2 * dk]
-              - 0.625 * x[ijk + 2 * di + dj + 2 * dk]
-              + 0.125 * x[ijk + 2 * di + 2 * dj + 2 * dk];
-    }
-  }
+  const int cols = bc_num_columns(G);
+  for (int c = tid; c < cols; c += nthreads) bc_v2_col(x, bc_column_offset(G, c), N.m, N.d[0], N.d[1], N.d[2]);
 }
-
 
 #endif

@@ -1,0 +1,209 @@
+/*
+ * bicgstab.cuh -- device body of the single-thread-block BiCGStab (see bicgstab.cu), shared with the
+ * coarse-grid cycle kernel (coarse.cu).
+ */
+#ifndef HPGMG_B200_BICGSTAB_CUH
+#define HPGMG_B200_BICGSTAB_CUH
+#include <math.h>
+#include "common.cuh"
+#include "stencil.cuh"
+#include "bc.cuh"
+
+#define BOTTOM_MAX_DIM   11
+#define BOTTOM_MAX_CELLS (BOTTOM_MAX_DIM * BOTTOM_MAX_DIM * BOTTOM_MAX_DIM)
+#define BOTTOM_THREADS   256   /* the stand-alone kernel; the body works for any 1-D block that is a multiple of 32 (<=1024) */
+
+struct BottomArgs {
+  DLevel L;
+  const BCItem *bc;             /* NO_CORNERS BC columns of the (single) box: flat table (device_level.cu) */
+  const ZeroItem *bcz;          /* every cell of those BC regions (zeroed first by the quadratic BC)          */
+  int nbc, nbcz;
+  int x_id, R_id;
+  double a, b, h2inv, rtol;
+  double *iters;                /* device scalar slot: iterations are added to it */
+};
+
+struct BottomCtx {
+  const BottomArgs &A;
+  double *prod;                 /* shared: BOTTOM_MAX_CELLS products / scratch */
+  double *red;                  /* shared: per-warp partials + broadcast slot  */
+  int n, cells, jS, kS;
+  __device__ int cell_offset(int c) const { return (c % n) + ((c / n) % n) * jS + (c / (n * n)) * kS; }
+};
+
+__device__ static void b_fill_ghosts(const BottomCtx &C, const int id)
+{
+  /* exchange_boundary is empty for a single box with Dirichlet BCs; apply_BCs = v4 (v2 if dim<4) */
+  const DLevel &L = C.A.L;
+  const bool v2 = C.n < 4;
+  if (v2) {
+    for (int e = threadIdx.x; e < C.A.nbcz; e += blockDim.x) L.vec(C.A.bcz[e].box, id)[C.A.bcz[e].cell] = 0.0;
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < C.A.nbc; e += blockDim.x) {
+    const BCItem it = C.A.bc[e];
+    const BCNormal N = bc_normal(it.subtype, L.jStride, L.kStride);
+    double *x = L.vec(it.box, id);
+    if (v2) bc_v2_col(x, it.ijk, N.m, N.d[0], N.d[1], N.d[2]);
+    else    bc_v4_column(x, it.ijk, N);
+  }
+  __syncthreads();
+}
+
+/* out = A in   (mode 0)   or   out = rhs - A in   (mode 1) */
+__device__ static void b_apply(const BottomCtx &C, const int out_id, const int in_id, const int rhs_id, const int mode)
+{
+  __syncthreads();
+  b_fill_ghosts(C, in_id);
+  const DLevel &L = C.A.L;
+  const double *x = L.vec(0, in_id), *bi = L.vec(0, VECTOR_BETA_I), *bj = L.vec(0, VECTOR_BETA_J), *bk = L.vec(0, VECTOR_BETA_K);
+  double *out = L.vec(0, out_id);
+  const double *rhs = L.vec(0, rhs_id);
+  for (int c = threadIdx.x; c < C.cells; c += blockDim.x) {
+    const int ijk = C.cell_offset(c);
+    const double Ax = fv4_apply_op(x + ijk, bi + ijk, bj + ijk, bk + ijk, C.jS, C.kS, C.A.b, C.A.h2inv);
+    out[ijk] = mode ? rhs[ijk] - Ax : Ax;
+  }
+  __syncthreads();
+}
+
+/* c = sa*a + sb*b */
+__device__ static void b_add(const BottomCtx &C, const int c_id, const double sa, const int a_id, const double sb, const int b_id)
+{
+  const DLevel &L = C.A.L;
+  double *c = L.vec(0, c_id);
+  const double *a = L.vec(0, a_id), *b = L.vec(0, b_id);
+  for (int q = threadIdx.x; q < C.cells; q += blockDim.x) {
+    const int ijk = C.cell_offset(q);
+    c[ijk] = sa * a[ijk] + sb * b[ijk];
+  }
+  __syncthreads();
+}
+__device__ static void b_scale(const BottomCtx &C, const int c_id, const double sa, const int a_id)
+{
+  const DLevel &L = C.A.L;
+  double *c = L.vec(0, c_id);
+  const double *a = L.vec(0, a_id);
+  for (int q = threadIdx.x; q < C.cells; q += blockDim.x) {
+    const int ijk = C.cell_offset(q);
+    c[ijk] = sa * a[ijk];
+  }
+  __syncthreads();
+}
+__device__ static void b_mul(const BottomCtx &C, const int c_id, const double s, const int a_id, const int b_id)
+{
+  const DLevel &L = C.A.L;
+  double *c = L.vec(0, c_id);
+  const double *a = L.vec(0, a_id), *b = L.vec(0, b_id);
+  for (int q = threadIdx.x; q < C.cells; q += blockDim.x) {
+    const int ijk = C.cell_offset(q);
+    c[ijk] = s * a[ijk] * b[ijk];
+  }
+  __syncthreads();
+}
+
+__device__ static double b_dot(const BottomCtx &C, const int a_id, const int b_id)
+{
+  const DLevel &L = C.A.L;
+  const double *a = L.vec(0, a_id), *b = L.vec(0, b_id);
+  for (int q = threadIdx.x; q < C.cells; q += blockDim.x) {
+    const int ijk = C.cell_offset(q);
+    C.prod[q] = a[ijk] * b[ijk];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int q = 0; q < C.cells; q++) s += C.prod[q];      /* k,j,i order == linear cell order */
+    C.red[32] = s;
+  }
+  __syncthreads();
+  const double r = C.red[32];
+  __syncthreads();
+  return r;
+}
+
+__device__ static double b_norm(const BottomCtx &C, const int a_id)
+{
+  const DLevel &L = C.A.L;
+  const double *a = L.vec(0, a_id);
+  double m = 0.0;
+  for (int q = threadIdx.x; q < C.cells; q += blockDim.x) {
+    const double f = fabs(a[C.cell_offset(q)]);
+    if (f > m) m = f;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double other = __shfl_down_sync(0xffffffffu, m, o);
+    if (other > m) m = other;
+  }
+  if ((threadIdx.x & 31) == 0) C.red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) if (C.red[w] > m) m = C.red[w];
+    C.red[32] = m;
+  }
+  __syncthreads();
+  const double r = C.red[32];
+  __syncthreads();
+  return r;
+}
+
+/* the whole solve, executed cooperatively by all threads of the calling thread block;
+ * prod: BOTTOM_MAX_CELLS doubles of shared memory, red: 33 doubles of shared memory */
+__device__ static void bicgstab_solve(const BottomArgs &A, double *prod, double *red)
+{
+  BottomCtx C = { A, prod, red, A.L.dim, A.L.dim * A.L.dim * A.L.dim, A.L.jStride, A.L.kStride };
+
+  const int r0 = VECTORS_RESERVED + 0, r = VECTORS_RESERVED + 1, p = VECTORS_RESERVED + 2, q = VECTORS_RESERVED + 3;
+  const int s = VECTORS_RESERVED + 4, t = VECTORS_RESERVED + 5, Ap = VECTORS_RESERVED + 6, As = VECTORS_RESERVED + 7;
+  const int x_id = A.x_id;
+  const int jMax = 200;
+  int j = 0;
+  bool failed = false, converged = false;
+
+  b_apply(C, r0, x_id, A.R_id, 1);                        /* r0 = R - A x */
+  b_scale(C, r, 1.0, r0);
+  b_scale(C, p, 1.0, r0);
+  double r_dot_r0 = b_dot(C, r, r0);
+  const double norm_of_r0 = b_norm(C, r);
+  if (r_dot_r0 == 0.0) converged = true;
+  if (norm_of_r0 == 0.0) converged = true;
+  while ((j < jMax) && !failed && !converged) {
+    j++;
+    b_mul(C, q, 1.0, VECTOR_DINV, p);                     /* q = D^-1 p */
+    b_apply(C, Ap, q, 0, 0);                              /* Ap = A q   */
+    const double Ap_dot_r0 = b_dot(C, Ap, r0);
+    if (Ap_dot_r0 == 0.0) { failed = true; break; }
+    const double alpha = r_dot_r0 / Ap_dot_r0;
+    if (isinf(alpha)) { failed = true; break; }
+    b_add(C, x_id, 1.0, x_id, alpha, q);
+    b_add(C, s, 1.0, r, -alpha, Ap);
+    const double norm_of_s = b_norm(C, s);
+    if (norm_of_s == 0.0) { converged = true; break; }
+    if (norm_of_s < A.rtol * norm_of_r0) { converged = true; break; }
+    b_mul(C, t, 1.0, VECTOR_DINV, s);                     /* t = D^-1 s */
+    b_apply(C, As, t, 0, 0);                              /* As = A t   */
+    const double As_dot_As = b_dot(C, As, As);
+    const double As_dot_s = b_dot(C, As, s);
+    if (As_dot_As == 0.0) { converged = true; break; }
+    const double omega = As_dot_s / As_dot_As;
+    if (omega == 0.0) { failed = true; break; }
+    if (isinf(omega)) { failed = true; break; }
+    b_add(C, x_id, 1.0, x_id, omega, t);
+    b_add(C, r, 1.0, s, -omega, As);
+    const double norm_of_r = b_norm(C, r);
+    if (norm_of_r == 0.0) { converged = true; break; }
+    if (norm_of_r < A.rtol * norm_of_r0) { converged = true; break; }
+    const double r_dot_r0_new = b_dot(C, r, r0);
+    if (r_dot_r0_new == 0.0) { failed = true; break; }
+    const double beta = (r_dot_r0_new / r_dot_r0) * (alpha / omega);
+    if (isinf(beta)) { failed = true; break; }
+    b_add(C, VECTOR_TEMP, 1.0, p, -omega, Ap);
+    b_add(C, p, 1.0, r, beta, VECTOR_TEMP);
+    r_dot_r0 = r_dot_r0_new;
+  }
+  if (threadIdx.x == 0) atomicAdd(A.iters, (double)j);
+}
+
+
+#endif

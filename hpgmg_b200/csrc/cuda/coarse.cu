@@ -1,0 +1,317 @@
+/*
+ * coarse.cu -- the coarse end of the multigrid cycle as ONE single-thread-block kernel.
+ *
+ * Levels of at most COARSE_MAX_CELLS cells (16^3 and coarser in the benchmark) carry ~4 % of the
+ * flops but ~75 % of the kernel launches of an F-cycle: every operator there
+ * is a few microseconds of launch latency around nanoseconds of work.  This kernel runs, for a
+ * chain of such levels c..bottom that live entirely on this GPU,
+ *
+ *   MODE_VCYCLE : MGVCycle(c)                                             (mg.c:1135-1164)
+ *   MODE_FTAIL  : the coarse tail of FMGSolve (mg.c:1285-1301): zero(e_bottom); bottom solve;
+ *                 for l = bottom-1 .. c: interpolation_fcycle(l <- l+1); MGVCycle(l)
+ *
+ * with __syncthreads() where the stream version has kernel boundaries.  Every step calls the SAME
+ * device bodies as the level-wide kernels (stencil.cuh, bc.cuh, bicgstab.cuh) or re-states their
+ * loops over the same block lists, so the bits are identical to the multi-launch path
+ * (tests/test_gpu_parity.py::test_coarse_kernel_equals_multilaunch_path).
+ */
+#include <math.h>
+#include "common.cuh"
+#include "stencil.cuh"
+#include "bc.cuh"
+#include "bicgstab.cuh"
+
+#define COARSE_MAX_LEVELS 8
+#define COARSE_THREADS    512
+
+enum { MODE_VCYCLE = 0, MODE_FTAIL = 1 };
+
+struct CoarseLevel {
+  DLevel L;
+  const int *low;
+  const CopyItem *xch[2];                         /* [0] NO_CORNERS, [1] BOX: one record per ghost cell copied   */
+  const BCItem *bc[2];                            /*                          one record per BC column            */
+  const ZeroItem *bcz[2];                         /*                          every cell of the BC regions (v2)   */
+  int n_xch[2], n_bc[2], n_bcz[2];
+  const blockCopy_type *restr, *interp;           /* local transfer lists */
+  int n_restr, n_interp;
+  double h2inv;
+  double c1[6], c2[6];                            /* Chebyshev coefficients of this level */
+};
+
+struct CoarseArgs {
+  int nlevels, mode, smoother, zero_bottom;
+  int e_id, R_id;
+  double a, b, rtol;
+  double *krylov;
+  CoarseLevel lv[COARSE_MAX_LEVELS];
+};
+
+/* ---- cooperative (whole thread block) versions of the level operators ---------------------------- */
+/* exchange_boundary + apply_BCs_v4 (or v2) for one shape, from the flat tables */
+__device__ static void c_fill_ghosts(const CoarseLevel &V, const int id, const bool box_shape, const bool force_v2)
+{
+  const DLevel &L = V.L;
+  const int w = box_shape ? 1 : 0;
+  const CopyItem *xc = V.xch[w];
+  for (int e = threadIdx.x; e < V.n_xch[w]; e += blockDim.x) {
+    const CopyItem c = xc[e];
+    L.vec(c.wbox, id)[c.wcell] = L.vec(c.rbox, id)[c.rcell];
+  }
+  __syncthreads();
+  const bool v2 = force_v2 || L.dim < 4;
+  if (v2) {                                                       /* boundary_fv.c:139-145: zero the regions first */
+    const ZeroItem *z = V.bcz[w];
+    for (int e = threadIdx.x; e < V.n_bcz[w]; e += blockDim.x) L.vec(z[e].box, id)[z[e].cell] = 0.0;
+    __syncthreads();
+  }
+  const BCItem *bc = V.bc[w];
+  for (int e = threadIdx.x; e < V.n_bc[w]; e += blockDim.x) {
+    const BCItem it = bc[e];
+    const BCNormal N = bc_normal(it.subtype, L.jStride, L.kStride);
+    double *x = L.vec(it.box, id);
+    if (v2) bc_v2_col(x, it.ijk, N.m, N.d[0], N.d[1], N.d[2]);
+    else    bc_v4_column(x, it.ijk, N);
+  }
+  __syncthreads();
+}
+
+/* one sweep / residual over every cell of every box.  mode: 0 GSRB sweep s, 1 Chebyshev sweep s, 2 residual */
+__device__ static void c_stencil(const CoarseLevel &V, const int mode, const int src, const int dst, const int rhs_id, const int s, const double b)
+{
+  const DLevel &L = V.L;
+  const int n = L.dim, cells = n * n * n, total = cells * L.nboxes;
+  for (int q = threadIdx.x; q < total; q += blockDim.x) {
+    const int box = q / cells, c = q - box * cells;
+    const int i = c % n, j = (c / n) % n, k = c / (n * n);
+    const int ijk = i + j * L.jStride + k * L.kStride;
+    const double *x = L.vec(box, src) + ijk;
+    double *out = L.vec(box, dst) + ijk;
+    if (mode == 0) {
+      const int color000 = (V.low[3 * box] ^ V.low[3 * box + 1] ^ V.low[3 * box + 2] ^ s) & 1;
+      if ((i ^ j ^ k ^ color000) & 1) { out[0] = x[0]; continue; }
+    }
+    const double Ax = fv4_apply_op(x, L.vec(box, VECTOR_BETA_I) + ijk, L.vec(box, VECTOR_BETA_J) + ijk, L.vec(box, VECTOR_BETA_K) + ijk, L.jStride, L.kStride, b, V.h2inv);
+    const double rhs = L.vec(box, rhs_id)[ijk];
+    if (mode == 2) { out[0] = rhs - Ax; continue; }
+    const double dinv = L.vec(box, VECTOR_DINV)[ijk];
+    if (mode == 0) out[0] = x[0] + dinv * (rhs - Ax);
+    else { const double xn = x[0]; out[0] = xn + V.c1[s] * (xn - out[0]) + V.c2[s] * dinv * (rhs - Ax); }
+  }
+  __syncthreads();
+}
+
+__device__ static void c_smooth(const CoarseArgs &A, const CoarseLevel &V, const int x_id, const int rhs_id)
+{
+  for (int s = 0; s < 6; s++) {
+    const int src = (s & 1) ? VECTOR_TEMP : x_id, dst = (s & 1) ? x_id : VECTOR_TEMP;
+    c_fill_ghosts(V, src, false, false);
+    c_stencil(V, A.smoother == HPGMG_SMOOTHER_CHEBY ? 1 : 0, src, dst, rhs_id, s, A.b);
+  }
+}
+
+__device__ static void c_zero(const DLevel &L, const int id)
+{
+  const int m = L.dim + 2 * L.ghosts, cells = m * m * m, total = cells * L.nboxes;
+  for (int q = threadIdx.x; q < total; q += blockDim.x) {
+    const int box = q / cells, c = q - box * cells;
+    const int i = c % m - L.ghosts, j = (c / m) % m - L.ghosts, k = c / (m * m) - L.ghosts;
+    L.vec(box, id)[i + j * L.jStride + k * L.kStride] = 0.0;
+  }
+  __syncthreads();
+}
+
+/* restriction.c:54-57 over the local list of the fine level */
+__device__ static void c_restrict_cell(const DLevel &Lc, const int id_c, const DLevel &Lf, const int id_f, const blockCopy_type *blocks, const int n)
+{
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int e = warp; e < n; e += nwarps) {                        /* one warp per list entry */
+    const blockCopy_type B = blocks[e];
+    const int rj = Lf.jStride, rk = Lf.kStride;
+    const double *rd = Lf.vec(B.read.box, id_f) + B.read.i + B.read.j * rj + B.read.k * rk;
+    double *wr = Lc.vec(B.write.box, id_c) + B.write.i + B.write.j * Lc.jStride + B.write.k * Lc.kStride;
+    const int di = B.dim.i, dj = B.dim.j, cells = di * dj * B.dim.k;
+    for (int c = lane; c < cells; c += 32) {
+      const int i = c % di, j = (c / di) % dj, k = c / (di * dj);
+      const double *r = rd + 2 * i + 2 * j * rj + 2 * k * rk;
+      wr[i + j * Lc.jStride + k * Lc.kStride] = (r[0] + r[1] + r[rj] + r[1 + rj] + r[rk] + r[1 + rk] + r[rj + rk] + r[1 + rj + rk]) * 0.125;
+    }
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void c_pro3(const double cm, const double c0, const double cp, double &lo, double &hi)
+{
+  const double c1 = 1.0 / 8.0;
+  lo = (c0 + c1 * (cm - cp));
+  hi = (c0 - c1 * (cm - cp));
+}
+__device__ __forceinline__ void c_pro5(const double cmm, const double cm, const double c0, const double cp, const double cpp, double &lo, double &hi)
+{
+  const double c2 = -3.0 / 128.0, c1 = 22.0 / 128.0;
+  lo = (c0 + c1 * (cm - cp) + c2 * (cmm - cpp));
+  hi = (c0 - c1 * (cm - cp) - c2 * (cmm - cpp));
+}
+
+/* interpolation_v2.c:112-172 (W=3) / interpolation_v4.c:149-238 (W=5) over the coarse level's local list */
+template <int W>
+__device__ static void c_interpolate(const DLevel &Lf, const int id_f, const double prescale, const DLevel &Lc, const int id_c, const blockCopy_type *blocks, const int n)
+{
+  constexpr int R = W / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int e = warp; e < n; e += nwarps) {                        /* one warp per list entry */
+    const blockCopy_type B = blocks[e];
+    const int rj = Lc.jStride, rk = Lc.kStride, wj = Lf.jStride, wk = Lf.kStride;
+    const double *rd = Lc.vec(B.read.box, id_c);
+    double *wr = Lf.vec(B.write.box, id_f);
+    const int di = B.dim.i, dj = B.dim.j, cells = di * dj * B.dim.k;
+    for (int c = lane; c < cells; c += 32) {
+      const int ii = c % di, jj = (c / di) % dj, kk = c / (di * dj);
+      const double *r = rd + (ii + B.read.i) + (jj + B.read.j) * rj + (kk + B.read.k) * rk;
+      double fi[2][W][W], fj[2][2][W];
+#pragma unroll
+      for (int K = 0; K < W; K++)
+#pragma unroll
+      for (int J = 0; J < W; J++) {
+        const double *p = r + (J - R) * rj + (K - R) * rk;
+        if constexpr (W == 3) c_pro3(p[-1], p[0], p[1], fi[0][J][K], fi[1][J][K]);
+        else                  c_pro5(p[-2], p[-1], p[0], p[1], p[2], fi[0][J][K], fi[1][J][K]);
+      }
+#pragma unroll
+      for (int K = 0; K < W; K++)
+#pragma unroll
+      for (int I = 0; I < 2; I++) {
+        if constexpr (W == 3) c_pro3(fi[I][0][K], fi[I][1][K], fi[I][2][K], fj[I][0][K], fj[I][1][K]);
+        else                  c_pro5(fi[I][0][K], fi[I][1][K], fi[I][2][K], fi[I][3][K], fi[I][W - 1][K], fj[I][0][K], fj[I][1][K]);
+      }
+      double *w = wr + (2 * ii + B.write.i) + (2 * jj + B.write.j) * wj + (2 * kk + B.write.k) * wk;
+#pragma unroll
+      for (int J = 0; J < 2; J++)
+#pragma unroll
+      for (int I = 0; I < 2; I++) {
+        double lo, hi;
+        if constexpr (W == 3) c_pro3(fj[I][J][0], fj[I][J][1], fj[I][J][2], lo, hi);
+        else                  c_pro5(fj[I][J][0], fj[I][J][1], fj[I][J][2], fj[I][J][3], fj[I][J][W - 1], lo, hi);
+        double *w0 = w + I + J * wj;
+        w0[0] = prescale * w0[0] + lo;
+        w0[wk] = prescale * w0[wk] + hi;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__device__ static void c_bottom_solve(const CoarseArgs &A, double *prod, double *red)
+{
+  const CoarseLevel &V = A.lv[A.nlevels - 1];
+  BottomArgs B;
+  B.L = V.L;  B.bc = V.bc[0];  B.nbc = V.n_bc[0];  B.bcz = V.bcz[0];  B.nbcz = V.n_bcz[0];
+  B.x_id = A.e_id;  B.R_id = A.R_id;  B.a = A.a;  B.b = A.b;  B.h2inv = V.h2inv;  B.rtol = A.rtol;  B.iters = A.krylov;
+  bicgstab_solve(B, prod, red);
+  __syncthreads();
+}
+
+/* MGVCycle(level c) for chain index c (mg.c:1135-1164), written as the two loops of the recursion */
+__device__ static void c_vcycle(const CoarseArgs &A, const int c, double *prod, double *red)
+{
+  const int bottom = A.nlevels - 1;
+  for (int l = c; l < bottom; l++) {
+    const CoarseLevel &V = A.lv[l], &Vc = A.lv[l + 1];
+    c_smooth(A, V, A.e_id, A.R_id);
+    c_fill_ghosts(V, A.e_id, false, false);                       /* residual(): exchange + BC on x */
+    c_stencil(V, 2, A.e_id, VECTOR_TEMP, A.R_id, 0, A.b);
+    c_restrict_cell(Vc.L, A.R_id, V.L, VECTOR_TEMP, V.restr, V.n_restr);
+    c_zero(Vc.L, A.e_id);
+  }
+  c_bottom_solve(A, prod, red);
+  for (int l = bottom - 1; l >= c; l--) {
+    const CoarseLevel &V = A.lv[l], &Vc = A.lv[l + 1];
+    c_fill_ghosts(Vc, A.e_id, true, true);                        /* interpolation_v2: exchange(BOX) + apply_BCs_v2 on the coarse level */
+    c_interpolate<3>(V.L, A.e_id, 1.0, Vc.L, A.e_id, Vc.interp, Vc.n_interp);
+    c_smooth(A, V, A.e_id, A.R_id);
+  }
+}
+
+__global__ void __launch_bounds__(COARSE_THREADS, 1) coarse_cycle_kernel(const __grid_constant__ CoarseArgs A)
+{
+  __shared__ double prod[BOTTOM_MAX_CELLS];
+  __shared__ double red[33];
+  if (A.mode == MODE_VCYCLE) {
+    c_vcycle(A, 0, prod, red);
+    return;
+  }
+  /* MODE_FTAIL: mg.c:1285-1301 restricted to the chain */
+  const int bottom = A.nlevels - 1;
+  if (A.zero_bottom) c_zero(A.lv[bottom].L, A.e_id);            /* mg.c:1285: only if the bottom is not the solve level */
+  c_bottom_solve(A, prod, red);
+  for (int l = bottom - 1; l >= 0; l--) {
+    const CoarseLevel &V = A.lv[l], &Vc = A.lv[l + 1];
+    c_fill_ghosts(Vc, A.e_id, true, false);                       /* interpolation_v4: exchange(BOX) + apply_BCs_v4 */
+    c_interpolate<5>(V.L, A.e_id, 0.0, Vc.L, A.e_id, Vc.interp, Vc.n_interp);
+    c_vcycle(A, l, prod, red);
+  }
+}
+
+/* ---- host side ------------------------------------------------------------------------------------ */
+static int g_coarse_enabled = -1;
+extern "C" void hpgmg_b200_use_coarse_kernel(int on) { g_coarse_enabled = on ? 1 : 0; }
+
+static int level_is_coarse_eligible(const level_type *level)
+{
+  if (level->num_ranks != 1 && level->num_my_boxes != level->boxes_in.i * level->boxes_in.j * level->boxes_in.k) return 0;
+  if (level->boundary_condition.type != BC_DIRICHLET || level->must_subtract_mean == 1) return 0;
+  if ((long)level->dim.i * level->dim.j * level->dim.k > COARSE_MAX_CELLS) return 0;
+  for (int s = 0; s < STENCIL_MAX_SHAPES; s++)
+    if (level->exchange_ghosts[s].num_sends || level->exchange_ghosts[s].num_recvs) return 0;
+  if (level->restriction[RESTRICT_CELL].num_sends || level->restriction[RESTRICT_CELL].num_recvs) return 0;
+  if (level->interpolation.num_sends || level->interpolation.num_recvs) return 0;
+  return 1;
+}
+
+/* Can levels `from`..bottom of this hierarchy run in the single-block kernel?  (all of them small,
+ * entirely local to this rank, Dirichlet, and a single-box bottom the BiCGStab body can solve) */
+extern "C" int hpgmg_coarse_chain_eligible(mg_type *MG, int from)
+{
+  if (g_coarse_enabled < 0) { const char *e = getenv("HPGMG_B200_NO_COARSE_KERNEL"); g_coarse_enabled = (e && atoi(e)) ? 0 : 1; }
+  if (!g_coarse_enabled) return 0;
+  const int bottom = MG->num_levels - 1;
+  if (from > bottom || bottom - from + 1 > COARSE_MAX_LEVELS) return 0;
+  for (int l = from; l <= bottom; l++) if (!level_is_coarse_eligible(MG->levels[l])) return 0;
+  const level_type *B = MG->levels[bottom];
+  if (B->num_my_boxes != 1 || B->boxes_in.i != 1 || B->box_dim > BOTTOM_MAX_DIM || B->box_dim < 2) return 0;
+  if (B->numVectors < VECTORS_RESERVED + 8) return 0;
+  return 1;
+}
+
+extern "C" void hpgmg_coarse_cycle(mg_type *MG, int from, int mode_ftail, int zero_bottom, int e_id, int R_id, double a, double b)
+{
+  static CoarseArgs A;                        /* 1.3 KB: passed by value as a __grid_constant__ parameter */
+  const int bottom = MG->num_levels - 1;
+  A.nlevels = bottom - from + 1;
+  A.mode = mode_ftail ? MODE_FTAIL : MODE_VCYCLE;
+  A.smoother = hpgmg_rt_smoother();
+  A.zero_bottom = zero_bottom;
+  A.e_id = e_id;  A.R_id = R_id;  A.a = a;  A.b = b;  A.rtol = MG_DEFAULT_BOTTOM_NORM;
+  A.krylov = hpgmg_rt_scalar_slots() + HPGMG_SLOT_KRYLOV;
+  for (int l = from; l <= bottom; l++) {
+    level_type *level = MG->levels[l];
+    hpgmg_device_level *D = HPGMG_DEV(level);
+    CoarseLevel &V = A.lv[l - from];
+    V.L = D->L;  V.low = D->low;
+    const int shapes[2] = { STENCIL_SHAPE_NO_CORNERS, STENCIL_SHAPE_BOX };
+    for (int w = 0; w < 2; w++) {
+      V.xch[w] = (const CopyItem *)D->copy_tab[shapes[w]].items;    V.n_xch[w] = D->copy_tab[shapes[w]].n;
+      V.bc[w] = (const BCItem *)D->bc_tab[shapes[w]].items;         V.n_bc[w] = D->bc_tab[shapes[w]].n;
+      V.bcz[w] = (const ZeroItem *)D->bczero_tab[shapes[w]].items;  V.n_bcz[w] = D->bczero_tab[shapes[w]].n;
+    }
+    V.restr = D->restriction[RESTRICT_CELL][1].blocks;           V.n_restr = D->restriction[RESTRICT_CELL][1].n;
+    V.interp = D->interpolation[1].blocks;                       V.n_interp = D->interpolation[1].n;
+    V.h2inv = 1.0 / (level->h * level->h);
+    /* Chebyshev coefficients exactly as chebyshev.c:22-40 */
+    double beta = 1.000 * level->dominant_eigenvalue_of_DinvA, alpha = 0.125000 * beta;
+    double theta = 0.5 * (beta + alpha), delta = 0.5 * (beta - alpha), sigma = theta / delta, rho_n = 1 / sigma;
+    V.c1[0] = 0.0;  V.c2[0] = 1 / theta;
+    for (int s = 1; s < 6; s++) { double rho_nm1 = rho_n; rho_n = 1.0 / (2.0 * sigma - rho_nm1); V.c1[s] = rho_n * rho_nm1; V.c2[s] = rho_n * 2.0 / delta; }
+  }
+  LAUNCH(coarse_cycle_kernel, 1, COARSE_THREADS, 0, A);
+}

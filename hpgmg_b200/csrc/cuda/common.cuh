@@ -54,7 +54,16 @@ struct DList {
   int n;
 };
 
-/* device mirror hanging off level_type::dev */
+/* Flat work tables of the small levels (<= COARSE_MAX_CELLS cells): the block lists expanded on the
+ * host into one record per ghost cell / BC column, so that a single thread block can spread the work
+ * over its threads without walking list entries one after the other (coarse.cu). */
+#define COARSE_MAX_CELLS 4096
+struct CopyItem { int rbox, rcell, wbox, wcell; };      /* cell offsets relative to cell (0,0,0) of a box vector */
+struct BCItem   { int box, subtype, ijk, pad; };        /* one BC column: nearest ghost cell + domain normal     */
+struct ZeroItem { int box, cell; };
+struct DTable   { void *items; int n; };
+
+/* device mirror hanging off level_type::fluxes */
 struct hpgmg_device_level {
   DLevel L;
   int   *low;                                   /* device [nboxes][3]: global coords of cell 0,0,0 */
@@ -62,6 +71,7 @@ struct hpgmg_device_level {
   DList  exchange[STENCIL_MAX_SHAPES][3];
   DList  restriction[4][3];
   DList  interpolation[3];
+  DTable copy_tab[STENCIL_MAX_SHAPES], bc_tab[STENCIL_MAX_SHAPES], bczero_tab[STENCIL_MAX_SHAPES];   /* small levels only */
   double *tile_partials;                        /* scratch for dot/mean: one double per compute tile */
   blockCopy_type *tiles;                        /* device copy of level->my_blocks                  */
   int     ntiles;

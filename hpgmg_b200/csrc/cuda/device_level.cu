@@ -4,6 +4,7 @@
  * walks with OpenMP: level.c:367-465 BCs, :498-922 ghost exchange, mg.c:181-831 transfers).
  */
 #include <string.h>
+#include <vector>
 #include "common.cuh"
 
 static void upload_list(DList *dst, const blockCopy_type *src, int n)
@@ -22,6 +23,57 @@ static void free_list(DList *l)
   if (l->blocks) CUDA_CHECK(cudaFree(l->blocks));
   l->blocks = NULL;
   l->n = 0;
+}
+
+static void upload_table(DTable *t, const void *host, int n, size_t item)
+{
+  t->items = NULL;
+  t->n = n;
+  if (n <= 0) return;
+  CUDA_CHECK(cudaMalloc(&t->items, (size_t)n * item));
+  CUDA_CHECK(cudaMemcpyAsync(t->items, host, (size_t)n * item, cudaMemcpyHostToDevice, g_stream));
+  CUDA_CHECK(cudaStreamSynchronize(g_stream));
+}
+
+/* expand the local ghost-exchange list and the BC list of every shape into per-cell / per-column records */
+static void build_small_level_tables(level_type *level, hpgmg_device_level *D)
+{
+  const int jS = level->box_jStride, kS = level->box_kStride, n = level->box_dim;
+  for (int s = 0; s < STENCIL_MAX_SHAPES; s++) {
+    std::vector<CopyItem> copies;
+    const blockCopy_type *xb = level->exchange_ghosts[s].blocks[1];
+    for (int e = 0; e < level->exchange_ghosts[s].num_blocks[1]; e++) {
+      const blockCopy_type &B = xb[e];
+      for (int k = 0; k < B.dim.k; k++) for (int j = 0; j < B.dim.j; j++) for (int i = 0; i < B.dim.i; i++) {
+        CopyItem c = { B.read.box, (B.read.i + i) + (B.read.j + j) * jS + (B.read.k + k) * kS,
+                       B.write.box, (B.write.i + i) + (B.write.j + j) * jS + (B.write.k + k) * kS };
+        copies.push_back(c);
+      }
+    }
+    std::vector<BCItem> cols;
+    std::vector<ZeroItem> zeros;
+    const blockCopy_type *bb = level->boundary_condition.blocks[s];
+    for (int e = 0; e < level->boundary_condition.num_blocks[s]; e++) {
+      const blockCopy_type &B = bb[e];
+      const int nrm[3] = { (B.subtype % 3) - 1, ((B.subtype % 9) / 3) - 1, (B.subtype / 9) - 1 };
+      const int lo[3] = { B.read.i, B.read.j, B.read.k }, ext[3] = { B.dim.i, B.dim.j, B.dim.k }, st[3] = { 1, jS, kS };
+      for (int k = 0; k < ext[2]; k++) for (int j = 0; j < ext[1]; j++) for (int i = 0; i < ext[0]; i++) {
+        ZeroItem z = { B.read.box, (lo[0] + i) + (lo[1] + j) * jS + (lo[2] + k) * kS };
+        zeros.push_back(z);
+      }
+      const int e0 = nrm[0] ? 1 : ext[0], e1 = nrm[1] ? 1 : ext[1], e2 = nrm[2] ? 1 : ext[2];
+      for (int c = 0; c < e0 * e1 * e2; c++) {
+        const int p[3] = { c % e0, (c / e0) % e1, c / (e0 * e1) };
+        int ijk = 0;
+        for (int a = 0; a < 3; a++) ijk += (nrm[a] ? (nrm[a] < 0 ? -1 : n) : p[a] + lo[a]) * st[a];
+        BCItem it = { B.read.box, B.subtype, ijk, 0 };
+        cols.push_back(it);
+      }
+    }
+    upload_table(&D->copy_tab[s], copies.data(), (int)copies.size(), sizeof(CopyItem));
+    upload_table(&D->bc_tab[s], cols.data(), (int)cols.size(), sizeof(BCItem));
+    upload_table(&D->bczero_tab[s], zeros.data(), (int)zeros.size(), sizeof(ZeroItem));
+  }
 }
 
 extern "C" void hpgmg_device_level_rebind_vectors(level_type *level)
@@ -64,6 +116,7 @@ extern "C" void hpgmg_device_level_create(level_type *level)
     for (int p = 0; p < 3; p++)
       upload_list(&D->exchange[s][p], level->exchange_ghosts[s].blocks[p], level->exchange_ghosts[s].num_blocks[p]);
   }
+  if ((long)level->dim.i * level->dim.j * level->dim.k <= COARSE_MAX_CELLS) build_small_level_tables(level, D);
   D->ntiles = level->num_my_blocks;
   if (D->ntiles > 0) {
     CUDA_CHECK(cudaMalloc(&D->tiles, (size_t)D->ntiles * sizeof(blockCopy_type)));
@@ -95,6 +148,11 @@ extern "C" void hpgmg_device_level_destroy(level_type *level)
   }
   for (int t = 0; t < 4; t++) for (int p = 0; p < 3; p++) free_list(&D->restriction[t][p]);
   for (int p = 0; p < 3; p++) free_list(&D->interpolation[p]);
+  for (int s = 0; s < STENCIL_MAX_SHAPES; s++) {
+    if (D->copy_tab[s].items) CUDA_CHECK(cudaFree(D->copy_tab[s].items));
+    if (D->bc_tab[s].items) CUDA_CHECK(cudaFree(D->bc_tab[s].items));
+    if (D->bczero_tab[s].items) CUDA_CHECK(cudaFree(D->bczero_tab[s].items));
+  }
   if (D->low) CUDA_CHECK(cudaFree(D->low));
   if (D->tiles) CUDA_CHECK(cudaFree(D->tiles));
   if (D->tile_partials) CUDA_CHECK(cudaFree(D->tile_partials));

@@ -118,7 +118,6 @@ static void launch_stencil(level_type *level, StencilArgs &A)
   }
   if (OP != OP_REBUILD && !g_force_generic) {
     if (n % 64 == 0) { launch_tiled<OP, 64, 8>(A); return; }
-    if (n % 32 == 0) { launch_tiled<OP, 32, 8>(A); return; }
   }
   dim3 block(n >= 32 ? 32 : (n >= 16 ? 16 : 8), n >= 32 ? 4 : 4, n >= 32 ? 2 : 4);
   const int ktiles = (n + block.z - 1) / block.z;

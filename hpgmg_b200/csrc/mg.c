@@ -490,6 +490,10 @@ void MGVCycle(mg_type *MG, int e_id, int R_id, double a, double b, int level)
 {
   level_type *L = MG->levels[level];
   if (!L->active) return;
+  if (hpgmg_coarse_chain_eligible(MG, level)) {          /* small, rank-local levels: the whole sub-cycle is one kernel */
+    hpgmg_coarse_cycle(MG, level, 0, 0, e_id, R_id, a, b);
+    return;
+  }
   if (level == MG->num_levels - 1) {
     IterativeSolver(L, e_id, R_id, a, b, MG_DEFAULT_BOTTOM_NORM);
     return;
@@ -555,9 +559,19 @@ static void enqueue_fcycle(mg_type *MG, int onLevel, int e_id, int R_id, int F_i
   for (int l = onLevel; l < MG->num_levels - 1; l++)
     restriction(MG->levels[l + 1], R_id, MG->levels[l], R_id, RESTRICT_CELL);
   int bottom = MG->num_levels - 1;
-  if (bottom > onLevel) zero_vector(MG->levels[bottom], e_id);
-  IterativeSolver(MG->levels[bottom], e_id, R_id, a, b, MG_DEFAULT_BOTTOM_NORM);
-  for (int l = MG->num_levels - 2; l >= onLevel; l--) {
+  /* the finest level from which everything down to the bottom can run in the single-block kernel */
+  int coarse_from = MG->num_levels;
+  for (int l = bottom; l >= onLevel && MG->levels[l]->active && hpgmg_coarse_chain_eligible(MG, l); l--) coarse_from = l;
+  int next = MG->num_levels - 2;
+  if (coarse_from <= bottom) {
+    /* zero(e_bottom); bottom solve; interpolation_fcycle + MGVCycle for l = bottom-1..coarse_from */
+    hpgmg_coarse_cycle(MG, coarse_from, 1, bottom > onLevel, e_id, R_id, a, b);
+    next = coarse_from - 1;
+  } else {
+    if (bottom > onLevel) zero_vector(MG->levels[bottom], e_id);
+    IterativeSolver(MG->levels[bottom], e_id, R_id, a, b, MG_DEFAULT_BOTTOM_NORM);
+  }
+  for (int l = next; l >= onLevel; l--) {
     interpolation_fcycle(MG->levels[l], e_id, 0.0, MG->levels[l + 1], e_id);
     MGVCycle(MG, e_id, R_id, a, b, l);
   }

@@ -45,6 +45,11 @@ void hpgmg_b200_set_verbose(int on);
  * graph and replay it.  0: plain stream launches (used by the per-operator timers). */
 void hpgmg_b200_use_graphs(int on);
 
+/* 1 (default): levels of <= 4096 cells that live entirely on this GPU run their whole sub-cycle
+ * (smooths, residual, transfers, bottom solve) inside ONE single-thread-block kernel instead of
+ * ~45 launches per level visit.  0: one launch per operator everywhere (same bits). */
+void hpgmg_b200_use_coarse_kernel(int on);
+
 /* 1: each operator synchronises and adds its device time to level->timers.* like the reference's
  * getTime() brackets (e.g. gsrb.c:37,130).  0 (default): timers only hold MGSolve totals. */
 void hpgmg_b200_profile_operators(int on);

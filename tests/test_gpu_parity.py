@@ -65,6 +65,32 @@ def test_graph_replay_equals_stream_launch(gpu_lib):
     gpu_lib.hpgmg_b200_use_graphs(1)
 
 
+@pytest.mark.parametrize("cfg,smoother", [("5 8", api.SMOOTHER_GSRB), ("4 27", api.SMOOTHER_GSRB), ("5 1", api.SMOOTHER_CHEBY)])
+def test_coarse_kernel_equals_multilaunch_path(gpu_lib, cfg, smoother):
+    """The single-block coarse-cycle kernel (coarse.cu) and the one-launch-per-operator path give the same bits
+    on every level (U, R, TEMP of all boxes)."""
+    log2, boxes = map(int, cfg.split())
+    snap = {}
+    for coarse in (0, 1):
+        gpu_lib.hpgmg_b200_use_coarse_kernel(coarse)
+        with api.Hierarchy(log2, boxes, smoother=smoother, use_graphs=False) as H:
+            launches0 = gpu_lib.hpgmg_b200_kernel_launches()
+            r = H.fmg_solve(0)
+            launches = gpu_lib.hpgmg_b200_kernel_launches() - launches0
+            arrays = [api.download(H.level(l), b, v).copy() for l in range(H.num_levels)
+                      for b in range(H.level(l).contents.num_my_boxes) for v in (api.VECTOR_U, api.VECTOR_R)]
+            its = H.level(H.num_levels - 1).contents.Krylov_iterations
+            snap[coarse] = (r, arrays, its, launches)
+    gpu_lib.hpgmg_b200_use_coarse_kernel(1)
+    gpu_lib.hpgmg_b200_set_smoother(api.SMOOTHER_GSRB)
+    assert snap[0][0] == snap[1][0] and snap[0][2] == snap[1][2]
+    for a, b in zip(snap[0][1], snap[1][1]):
+        n = a.shape[0] - 4
+        s = slice(2, 2 + n)
+        np.testing.assert_array_equal(a[s, s, s], b[s, s, s])
+    assert snap[1][3] < snap[0][3] / 2, "the coarse kernel should remove most launches"
+
+
 def test_fmg_solve_host_buffers(gpu_lib):
     """The end-to-end entry point with HOST buffers (what bench.py's e2e times)."""
     with api.Hierarchy(5, 8) as H:
