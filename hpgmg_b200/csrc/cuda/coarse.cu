@@ -37,6 +37,8 @@ struct CoarseLevel {
   int n_restr, n_interp;
   double h2inv;
   double c1[6], c2[6];                            /* Chebyshev coefficients of this level */
+  int smem_offset;                                /* >=0: the level's whole slab lives in shared memory during the kernel (doubles) */
+  int slab_doubles;
 };
 
 struct CoarseArgs {
@@ -232,39 +234,85 @@ __device__ static void c_vcycle(const CoarseArgs &A, const int c, double *prod, 
   }
 }
 
-__global__ void __launch_bounds__(COARSE_THREADS, 1) coarse_cycle_kernel(const __grid_constant__ CoarseArgs A)
+/* The coarsest levels (8^3, 4^3, 2^3 in the benchmark: 200 KB with all their vectors) are copied into
+ * shared memory for the duration of the kernel: DLevel::base is simply pointed at the copy, so every
+ * operator body works on it unchanged, at shared-memory instead of L2 latency.  Everything except the
+ * read-only operator data (Dinv, betas) is written back at the end. */
+__global__ void __launch_bounds__(COARSE_THREADS, 1) coarse_cycle_kernel(const __grid_constant__ CoarseArgs Ain)
 {
-  __shared__ double prod[BOTTOM_MAX_CELLS];
-  __shared__ double red[33];
+  extern __shared__ __align__(16) double dyn[];
+  CoarseArgs &A = *reinterpret_cast<CoarseArgs *>(dyn);
+  constexpr int ARGS_DOUBLES = (int)((sizeof(CoarseArgs) + 15) / 16) * 2;
+  double *prod = dyn + ARGS_DOUBLES;
+  double *red = prod + BOTTOM_MAX_CELLS + 1;
+  double *pool = red + 34;
+
+  {                                                                /* stage the arguments, then patch the resident levels */
+    const int *src = reinterpret_cast<const int *>(&Ain);
+    int *dst = reinterpret_cast<int *>(dyn);
+    for (int w = threadIdx.x; w < (int)(sizeof(CoarseArgs) / sizeof(int)); w += blockDim.x) dst[w] = src[w];
+  }
+  __syncthreads();
+  for (int l = 0; l < Ain.nlevels; l++) {
+    const CoarseLevel &G = Ain.lv[l];
+    if (G.smem_offset < 0) continue;
+    double *copy = pool + G.smem_offset;
+    const double2 *g2 = reinterpret_cast<const double2 *>(G.L.base);
+    double2 *c2 = reinterpret_cast<double2 *>(copy);
+    for (int q = threadIdx.x; q < G.slab_doubles / 2; q += blockDim.x) c2[q] = g2[q];
+    if (threadIdx.x == 0) A.lv[l].L.base = copy;
+  }
+  __syncthreads();
+
   if (A.mode == MODE_VCYCLE) {
     c_vcycle(A, 0, prod, red);
-    return;
+  } else {                                                          /* MODE_FTAIL: mg.c:1285-1301 restricted to the chain */
+    const int bottom = A.nlevels - 1;
+    if (A.zero_bottom) c_zero(A.lv[bottom].L, A.e_id);              /* mg.c:1285: only if the bottom is not the solve level */
+    c_bottom_solve(A, prod, red);
+    for (int l = bottom - 1; l >= 0; l--) {
+      const CoarseLevel &V = A.lv[l], &Vc = A.lv[l + 1];
+      c_fill_ghosts(Vc, A.e_id, true, false);                       /* interpolation_v4: exchange(BOX) + apply_BCs_v4 */
+      c_interpolate<5>(V.L, A.e_id, 0.0, Vc.L, A.e_id, Vc.interp, Vc.n_interp);
+      c_vcycle(A, l, prod, red);
+    }
   }
-  /* MODE_FTAIL: mg.c:1285-1301 restricted to the chain */
-  const int bottom = A.nlevels - 1;
-  if (A.zero_bottom) c_zero(A.lv[bottom].L, A.e_id);            /* mg.c:1285: only if the bottom is not the solve level */
-  c_bottom_solve(A, prod, red);
-  for (int l = bottom - 1; l >= 0; l--) {
-    const CoarseLevel &V = A.lv[l], &Vc = A.lv[l + 1];
-    c_fill_ghosts(Vc, A.e_id, true, false);                       /* interpolation_v4: exchange(BOX) + apply_BCs_v4 */
-    c_interpolate<5>(V.L, A.e_id, 0.0, Vc.L, A.e_id, Vc.interp, Vc.n_interp);
-    c_vcycle(A, l, prod, red);
+
+  __syncthreads();
+  for (int l = 0; l < Ain.nlevels; l++) {                           /* write the resident levels back */
+    const CoarseLevel &G = Ain.lv[l];
+    if (G.smem_offset < 0) continue;
+    const DLevel &L = G.L;
+    const double *copy = pool + G.smem_offset;
+    const int per_vec = L.volume / 2;                               /* volume is a multiple of 4 doubles */
+    for (int bv = 0; bv < L.nboxes * L.nvec; bv++) {
+      const int v = bv % L.nvec;
+      if (v == VECTOR_DINV || v == VECTOR_BETA_I || v == VECTOR_BETA_J || v == VECTOR_BETA_K) continue;
+      const double2 *c2 = reinterpret_cast<const double2 *>(copy + (size_t)bv * L.volume);
+      double2 *g2 = reinterpret_cast<double2 *>(L.base + (size_t)bv * L.volume);
+      for (int q = threadIdx.x; q < per_vec; q += blockDim.x) g2[q] = c2[q];
+    }
   }
 }
 
 /* ---- host side ------------------------------------------------------------------------------------ */
 static int g_coarse_enabled = -1;
+static int g_coarse_smem = 1;
+/* single-block cycles pay off up to 8^3 (one cell per thread, latency-bound); 16^3 is faster as separate launches */
+static long g_coarse_max_cells = 512;
+extern "C" void hpgmg_b200_coarse_levels_in_smem(int on) { g_coarse_smem = on ? 1 : 0; }
 extern "C" void hpgmg_b200_use_coarse_kernel(int on) { g_coarse_enabled = on ? 1 : 0; }
 
-static int level_is_coarse_eligible(const level_type *level)
+static int level_is_coarse_eligible(const level_type *level, int is_top, int is_bottom)
 {
-  if (level->num_ranks != 1 && level->num_my_boxes != level->boxes_in.i * level->boxes_in.j * level->boxes_in.k) return 0;
+  if (level->num_my_boxes != level->boxes_in.i * level->boxes_in.j * level->boxes_in.k) return 0;   /* every box of the level is mine */
   if (level->boundary_condition.type != BC_DIRICHLET || level->must_subtract_mean == 1) return 0;
-  if ((long)level->dim.i * level->dim.j * level->dim.k > COARSE_MAX_CELLS) return 0;
+  if ((long)level->dim.i * level->dim.j * level->dim.k > g_coarse_max_cells) return 0;
   for (int s = 0; s < STENCIL_MAX_SHAPES; s++)
     if (level->exchange_ghosts[s].num_sends || level->exchange_ghosts[s].num_recvs) return 0;
-  if (level->restriction[RESTRICT_CELL].num_sends || level->restriction[RESTRICT_CELL].num_recvs) return 0;
-  if (level->interpolation.num_sends || level->interpolation.num_recvs) return 0;
+  /* transfers BETWEEN chain levels must be local; those across the top of the chain run outside the kernel */
+  if (!is_bottom && (level->restriction[RESTRICT_CELL].num_sends || level->interpolation.num_recvs)) return 0;
+  if (!is_top && (level->restriction[RESTRICT_CELL].num_recvs || level->interpolation.num_sends)) return 0;
   return 1;
 }
 
@@ -272,11 +320,16 @@ static int level_is_coarse_eligible(const level_type *level)
  * entirely local to this rank, Dirichlet, and a single-box bottom the BiCGStab body can solve) */
 extern "C" int hpgmg_coarse_chain_eligible(mg_type *MG, int from)
 {
-  if (g_coarse_enabled < 0) { const char *e = getenv("HPGMG_B200_NO_COARSE_KERNEL"); g_coarse_enabled = (e && atoi(e)) ? 0 : 1; }
+  if (g_coarse_enabled < 0) {
+    const char *e = getenv("HPGMG_B200_NO_COARSE_KERNEL");
+    g_coarse_enabled = (e && atoi(e)) ? 0 : 1;
+    const char *m = getenv("HPGMG_B200_COARSE_MAX_CELLS");
+    if (m && atol(m) > 0) g_coarse_max_cells = atol(m) > COARSE_MAX_CELLS ? COARSE_MAX_CELLS : atol(m);
+  }
   if (!g_coarse_enabled) return 0;
   const int bottom = MG->num_levels - 1;
   if (from > bottom || bottom - from + 1 > COARSE_MAX_LEVELS) return 0;
-  for (int l = from; l <= bottom; l++) if (!level_is_coarse_eligible(MG->levels[l])) return 0;
+  for (int l = from; l <= bottom; l++) if (!level_is_coarse_eligible(MG->levels[l], l == from, l == bottom)) return 0;
   const level_type *B = MG->levels[bottom];
   if (B->num_my_boxes != 1 || B->boxes_in.i != 1 || B->box_dim > BOTTOM_MAX_DIM || B->box_dim < 2) return 0;
   if (B->numVectors < VECTORS_RESERVED + 8) return 0;
@@ -313,5 +366,26 @@ extern "C" void hpgmg_coarse_cycle(mg_type *MG, int from, int mode_ftail, int ze
     V.c1[0] = 0.0;  V.c2[0] = 1 / theta;
     for (int s = 1; s < 6; s++) { double rho_nm1 = rho_n; rho_n = 1.0 / (2.0 * sigma - rho_nm1); V.c1[s] = rho_n * rho_nm1; V.c2[s] = rho_n * 2.0 / delta; }
   }
-  LAUNCH(coarse_cycle_kernel, 1, COARSE_THREADS, 0, A);
+  /* residency: from the bottom up while the slabs fit in the 227 KB of one SM */
+  const size_t fixed = sizeof(double) * (size_t)(((sizeof(CoarseArgs) + 15) / 16) * 2 + BOTTOM_MAX_CELLS + 1 + 34);
+  const size_t budget = 232448 - fixed;
+  size_t used = 0;
+  for (int l = bottom; l >= from; l--) {
+    CoarseLevel &V = A.lv[l - from];
+    const size_t doubles = (size_t)V.L.nboxes * V.L.nvec * V.L.volume;
+    V.slab_doubles = (int)doubles;
+    V.smem_offset = -1;
+    if (g_coarse_smem && (used + doubles) * sizeof(double) <= budget && (doubles % 2) == 0 && ((uintptr_t)V.L.base % 16) == 0) {
+      V.smem_offset = (int)used;
+      used += doubles;
+    } else break;                                                    /* keep the resident set contiguous from the bottom */
+  }
+  for (int l = from; l <= bottom; l++) if (A.lv[l - from].smem_offset < 0) { A.lv[l - from].smem_offset = -1; }
+  const size_t smem = fixed + used * sizeof(double);
+  static size_t configured = 0;
+  if (smem > configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(coarse_cycle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    configured = 232448;
+  }
+  LAUNCH(coarse_cycle_kernel, 1, COARSE_THREADS, smem, A);
 }

@@ -49,6 +49,9 @@ void hpgmg_b200_use_graphs(int on);
  * (smooths, residual, transfers, bottom solve) inside ONE single-thread-block kernel instead of
  * ~45 launches per level visit.  0: one launch per operator everywhere (same bits). */
 void hpgmg_b200_use_coarse_kernel(int on);
+/* 1 (default): inside that kernel the coarsest levels (as many as fit in 227 KB, from the bottom up)
+ * are held in shared memory.  0: they stay in global memory (same bits; for A/B timing). */
+void hpgmg_b200_coarse_levels_in_smem(int on);
 
 /* 1: each operator synchronises and adds its device time to level->timers.* like the reference's
  * getTime() brackets (e.g. gsrb.c:37,130).  0 (default): timers only hold MGSolve totals. */

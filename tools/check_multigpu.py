@@ -1,0 +1,28 @@
+"""Run under torchrun (one rank per GPU): build `hpgmg-fv <log2> <boxes_per_rank>` across the ranks, run the
+driver's Richardson pass and compare with the goldens of the equivalent single-process reference run
+(an N-rank run has the same boxes as a 1-rank run with N x the boxes)."""
+import json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import hpgmg_b200.api as api
+
+log2 = int(sys.argv[1]) if len(sys.argv) > 1 else 5
+bpr = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+graphs = not (len(sys.argv) > 3 and sys.argv[3] == "nograph")
+rank, world = api.init_distributed()
+L = api.lib()
+H = api.Hierarchy(log2, bpr, my_rank=rank, num_ranks=world, use_graphs=graphs)
+err, order, norms = H.richardson()
+boxes = H.boxes_in_i ** 3
+gold = json.load(open(os.path.join(ROOT, "tests", "golden", "goldens.json")))["solves"].get(f"{log2} {boxes} gsrb")
+if rank == 0:
+    ok = gold is not None and [n[0] for n in norms] == gold["norms"] and err == gold["error"]
+    print(f"world={world} cfg={log2} {bpr}/rank -> {boxes} boxes, levels={H.num_levels} graphs={graphs}")
+    print("  norms", [repr(n[0]) for n in norms], "error", repr(err), "order", round(order, 3))
+    print("  golden", gold["norms"] if gold else None, gold["error"] if gold else None)
+    print("  PARITY", "OK (bit-exact)" if ok else "MISMATCH")
+H.close()
+if world > 1:
+    import torch.distributed as dist
+    L.hpgmg_b200_comm_finalize()
+    dist.destroy_process_group()
