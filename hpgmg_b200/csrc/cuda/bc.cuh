@@ -23,32 +23,35 @@ __device__ __forceinline__ void quartic_pair(const double x1, const double x2, c
 }
 
 /* ---- one column, quartic ------------------------------------------------------------------------ */
-/* x points at cell (0,0,0) of the box vector, ijk is the offset of the column's nearest ghost cell,
- * d0<d1<d2 (axis order) are the inward strides of the normal axes. */
-__device__ __forceinline__ void bc_v4_col1(double *x, const int ijk, const int d0)
+/* w points at the column's nearest ghost cell; r points at the SAME position in the array the interior
+ * values are read from: the box itself, or -- when the column's tangential coordinates lie in a ghost
+ * region that exchange_boundary would fill -- the image of that position inside the neighbouring
+ * box (fused ghost fill, ghost.cu: same values, no dependency on the copy).  d0<d1<d2 (axis order) are
+ * the inward strides of the normal axes; both boxes share the strides. */
+__device__ __forceinline__ void bc_v4_col1(const double *r, double *w, const int d0)
 {
   double n, f;
-  quartic_pair(x[ijk + d0], x[ijk + 2 * d0], x[ijk + 3 * d0], x[ijk + 4 * d0], n, f);
-  x[ijk] = n;
-  x[ijk - d0] = f;
+  quartic_pair(r[d0], r[2 * d0], r[3 * d0], r[4 * d0], n, f);
+  w[0] = n;
+  w[-d0] = f;
 }
-__device__ __forceinline__ void bc_v4_col2(double *x, const int ijk, const int d0, const int d1)
+__device__ __forceinline__ void bc_v4_col2(const double *r, double *w, const int d0, const int d1)
 {
   double n[4], f[4];
 #pragma unroll
   for (int J = 0; J < 4; J++) {
-    const int o = ijk + (J + 1) * d1;
-    quartic_pair(x[o + d0], x[o + 2 * d0], x[o + 3 * d0], x[o + 4 * d0], n[J], f[J]);
+    const double *o = r + (J + 1) * d1;
+    quartic_pair(o[d0], o[2 * d0], o[3 * d0], o[4 * d0], n[J], f[J]);
   }
   double nn, nf, fn, ff;
   quartic_pair(n[0], n[1], n[2], n[3], nn, nf);
   quartic_pair(f[0], f[1], f[2], f[3], fn, ff);
-  x[ijk] = nn;
-  x[ijk - d1] = nf;
-  x[ijk - d0] = fn;
-  x[ijk - d0 - d1] = ff;
+  w[0] = nn;
+  w[-d1] = nf;
+  w[-d0] = fn;
+  w[-d0 - d1] = ff;
 }
-__device__ __forceinline__ void bc_v4_col3(double *x, const int ijk, const int d0, const int d1, const int d2)
+__device__ __forceinline__ void bc_v4_col3(const double *r, double *w, const int d0, const int d1, const int d2)
 {
   double nn[4], nf[4], fn[4], ff[4];
 #pragma unroll
@@ -56,8 +59,8 @@ __device__ __forceinline__ void bc_v4_col3(double *x, const int ijk, const int d
     double n[4], f[4];
 #pragma unroll
     for (int J = 0; J < 4; J++) {
-      const int o = ijk + (J + 1) * d1 + (K + 1) * d2;
-      quartic_pair(x[o + d0], x[o + 2 * d0], x[o + 3 * d0], x[o + 4 * d0], n[J], f[J]);
+      const double *o = r + (J + 1) * d1 + (K + 1) * d2;
+      quartic_pair(o[d0], o[2 * d0], o[3 * d0], o[4 * d0], n[J], f[J]);
     }
     quartic_pair(n[0], n[1], n[2], n[3], nn[K], nf[K]);
     quartic_pair(f[0], f[1], f[2], f[3], fn[K], ff[K]);
@@ -67,36 +70,46 @@ __device__ __forceinline__ void bc_v4_col3(double *x, const int ijk, const int d
   quartic_pair(nf[0], nf[1], nf[2], nf[3], nfn, nff);
   quartic_pair(fn[0], fn[1], fn[2], fn[3], fnn, fnf);
   quartic_pair(ff[0], ff[1], ff[2], ff[3], ffn, fff);
-  x[ijk] = nnn;
-  x[ijk - d2] = nnf;
-  x[ijk - d1] = nfn;
-  x[ijk - d1 - d2] = nff;
-  x[ijk - d0] = fnn;
-  x[ijk - d0 - d2] = fnf;
-  x[ijk - d0 - d1] = ffn;
-  x[ijk - d0 - d1 - d2] = fff;
+  w[0] = nnn;
+  w[-d2] = nnf;
+  w[-d1] = nfn;
+  w[-d1 - d2] = nff;
+  w[-d0] = fnn;
+  w[-d0 - d2] = fnf;
+  w[-d0 - d1] = ffn;
+  w[-d0 - d1 - d2] = fff;
 }
 
 /* ---- one column, quadratic: only the nearest ghost cell (boundary_fv.c:169, :206-209, :238-245) ---- */
-__device__ __forceinline__ void bc_v2_col(double *x, const int ijk, const int m, const int d0, const int d1, const int d2)
+__device__ __forceinline__ double bc_v2_value(const double *r, const int m, const int d0, const int d1, const int d2)
 {
-  if (m == 1) {
-    x[ijk] = -2.5 * x[ijk + d0] + 0.5 * x[ijk + 2 * d0];
-  } else if (m == 2) {
-    x[ijk] = 6.25 * x[ijk + d0 + d1]
-           - 1.25 * x[ijk + 2 * d0 + d1]
-           - 1.25 * x[ijk + d0 + 2 * d1]
-           + 0.25 * x[ijk + 2 * d0 + 2 * d1];
-  } else {
-    x[ijk] = -15.625 * x[ijk + d0 + d1 + d2]
-            + 3.125 * x[ijk + 2 * d0 + d1 + d2]
-            + 3.125 * x[ijk + d0 + 2 * d1 + d2]
-            + 3.125 * x[ijk + d0 + d1 + 2 * d2]
-            - 0.625 * x[ijk + 2 * d0 + 2 * d1 + d2]
-            - 0.625 * x[ijk + d0 + 2 * d1 + 2 * d2]
-            - 0.625 * x[ijk + 2 * d0 + d1 + 2 * d2]
-            + 0.125 * x[ijk + 2 * d0 + 2 * d1 + 2 * d2];
-  }
+  if (m == 1) return -2.5 * r[d0] + 0.5 * r[2 * d0];
+  if (m == 2) return 6.25 * r[d0 + d1]
+                   - 1.25 * r[2 * d0 + d1]
+                   - 1.25 * r[d0 + 2 * d1]
+                   + 0.25 * r[2 * d0 + 2 * d1];
+  return -15.625 * r[d0 + d1 + d2]
+        + 3.125 * r[2 * d0 + d1 + d2]
+        + 3.125 * r[d0 + 2 * d1 + d2]
+        + 3.125 * r[d0 + d1 + 2 * d2]
+        - 0.625 * r[2 * d0 + 2 * d1 + d2]
+        - 0.625 * r[d0 + 2 * d1 + 2 * d2]
+        - 0.625 * r[2 * d0 + d1 + 2 * d2]
+        + 0.125 * r[2 * d0 + 2 * d1 + 2 * d2];
+}
+__device__ __forceinline__ void bc_v2_col(const double *r, double *w, const int m, const int d0, const int d1, const int d2)
+{
+  w[0] = bc_v2_value(r, m, d0, d1, d2);
+}
+/* the same, plus the zeroing of the column's deeper ghost cells (boundary_fv.c:139-145 zeroes the whole
+ * region first; with 2 ghost layers a region is exactly the union of its columns' 2^m cells) */
+__device__ __forceinline__ void bc_v2_col_zero_rest(const double *r, double *w, const int m, const int d0, const int d1, const int d2)
+{
+  const double v = bc_v2_value(r, m, d0, d1, d2);
+  w[-d0] = 0.0;
+  if (m >= 2) { w[-d1] = 0.0; w[-d0 - d1] = 0.0; }
+  if (m >= 3) { w[-d2] = 0.0; w[-d0 - d2] = 0.0; w[-d1 - d2] = 0.0; w[-d0 - d1 - d2] = 0.0; }
+  w[0] = v;
 }
 
 /* the normal axes of a domain normal `subtype` (0..26 = 13+di+3dj+9dk): their count and inward strides */
@@ -118,11 +131,11 @@ __device__ __forceinline__ BCNormal bc_normal(const int subtype, const int jS, c
     if (N.normal[a]) N.d[N.m++] = (N.normal[a] < 0) ? stride[a] : -stride[a];
   return N;
 }
-__device__ __forceinline__ void bc_v4_column(double *x, const int ijk, const BCNormal &N)
+__device__ __forceinline__ void bc_v4_column(const double *r, double *w, const BCNormal &N)
 {
-  if (N.m == 1)      bc_v4_col1(x, ijk, N.d[0]);
-  else if (N.m == 2) bc_v4_col2(x, ijk, N.d[0], N.d[1]);
-  else               bc_v4_col3(x, ijk, N.d[0], N.d[1], N.d[2]);
+  if (N.m == 1)      bc_v4_col1(r, w, N.d[0]);
+  else if (N.m == 2) bc_v4_col2(r, w, N.d[0], N.d[1]);
+  else               bc_v4_col3(r, w, N.d[0], N.d[1], N.d[2]);
 }
 
 /* ---- one list entry (a block of columns), cooperatively by nthreads threads ---------------------- */
@@ -177,7 +190,7 @@ __device__ __forceinline__ void bc_v4_block(const DLevel &L, const int id, const
     __syncthreads();
   }
   const int cols = bc_num_columns(G);
-  for (int c = tid; c < cols; c += nthreads) bc_v4_column(x, bc_column_offset(G, c), N);
+  for (int c = tid; c < cols; c += nthreads) { double *w = x + bc_column_offset(G, c); bc_v4_column(w, w, N); }
 }
 
 /* quadratic: deeper ghost layers are zeroed first (boundary_fv.c:139-145) */
@@ -191,7 +204,7 @@ __device__ __forceinline__ void bc_v2_block(const DLevel &L, const int id, const
     __syncthreads();
   }
   const int cols = bc_num_columns(G);
-  for (int c = tid; c < cols; c += nthreads) bc_v2_col(x, bc_column_offset(G, c), N.m, N.d[0], N.d[1], N.d[2]);
+  for (int c = tid; c < cols; c += nthreads) { double *w = x + bc_column_offset(G, c); bc_v2_col(w, w, N.m, N.d[0], N.d[1], N.d[2]); }
 }
 
 #endif

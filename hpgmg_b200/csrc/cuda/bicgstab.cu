@@ -33,8 +33,8 @@ extern "C" int hpgmg_bicgstab_device(level_type *level, int x_id, int R_id, doub
   hpgmg_device_level *D = HPGMG_DEV(level);
   BottomArgs A;
   A.L = D->L;
-  A.bc = (const BCItem *)D->bc_tab[STENCIL_SHAPE_NO_CORNERS].items;       A.nbc = D->bc_tab[STENCIL_SHAPE_NO_CORNERS].n;
-  A.bcz = (const ZeroItem *)D->bczero_tab[STENCIL_SHAPE_NO_CORNERS].items;  A.nbcz = D->bczero_tab[STENCIL_SHAPE_NO_CORNERS].n;
+  if (D->fill_nvec != level->numVectors || D->fill[STENCIL_SHAPE_NO_CORNERS].nlate > 0) return 0;
+  A.bc = D->fill[STENCIL_SHAPE_NO_CORNERS].bc;  A.nbc = D->fill[STENCIL_SHAPE_NO_CORNERS].nbc;
   A.x_id = x_id;  A.R_id = R_id;  A.a = a;  A.b = b;
   A.h2inv = 1.0 / (level->h * level->h);
   A.rtol = rtol;

@@ -15,9 +15,8 @@
 
 struct BottomArgs {
   DLevel L;
-  const BCItem *bc;             /* NO_CORNERS BC columns of the (single) box: flat table (device_level.cu) */
-  const ZeroItem *bcz;          /* every cell of those BC regions (zeroed first by the quadratic BC)          */
-  int nbc, nbcz;
+  const FillBC *bc;             /* NO_CORNERS BC columns of the (single) box: flat table (device_level.cu) */
+  int nbc;
   int x_id, R_id;
   double a, b, h2inv, rtol;
   double *iters;                /* device scalar slot: iterations are added to it */
@@ -35,17 +34,13 @@ __device__ static void b_fill_ghosts(const BottomCtx &C, const int id)
 {
   /* exchange_boundary is empty for a single box with Dirichlet BCs; apply_BCs = v4 (v2 if dim<4) */
   const DLevel &L = C.A.L;
+  double *v = L.base + (size_t)id * (size_t)L.volume;
   const bool v2 = C.n < 4;
-  if (v2) {
-    for (int e = threadIdx.x; e < C.A.nbcz; e += blockDim.x) L.vec(C.A.bcz[e].box, id)[C.A.bcz[e].cell] = 0.0;
-    __syncthreads();
-  }
   for (int e = threadIdx.x; e < C.A.nbc; e += blockDim.x) {
-    const BCItem it = C.A.bc[e];
+    const FillBC it = C.A.bc[e];
     const BCNormal N = bc_normal(it.subtype, L.jStride, L.kStride);
-    double *x = L.vec(it.box, id);
-    if (v2) bc_v2_col(x, it.ijk, N.m, N.d[0], N.d[1], N.d[2]);
-    else    bc_v4_column(x, it.ijk, N);
+    if (v2) bc_v2_col_zero_rest(v + it.src, v + it.dst, N.m, N.d[0], N.d[1], N.d[2]);
+    else    bc_v4_column(v + it.src, v + it.dst, N);
   }
   __syncthreads();
 }

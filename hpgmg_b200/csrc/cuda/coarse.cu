@@ -29,10 +29,9 @@ enum { MODE_VCYCLE = 0, MODE_FTAIL = 1 };
 struct CoarseLevel {
   DLevel L;
   const int *low;
-  const CopyItem *xch[2];                         /* [0] NO_CORNERS, [1] BOX: one record per ghost cell copied   */
-  const BCItem *bc[2];                            /*                          one record per BC column            */
-  const ZeroItem *bcz[2];                         /*                          every cell of the BC regions (v2)   */
-  int n_xch[2], n_bc[2], n_bcz[2];
+  const FillCopy *xch[2];                         /* [0] NO_CORNERS, [1] BOX: one record per ghost cell copied   */
+  const FillBC *bc[2];                            /*                          one record per BC column            */
+  int n_xch[2], n_bc[2];
   const blockCopy_type *restr, *interp;           /* local transfer lists */
   int n_restr, n_interp;
   double h2inv;
@@ -50,30 +49,25 @@ struct CoarseArgs {
 };
 
 /* ---- cooperative (whole thread block) versions of the level operators ---------------------------- */
-/* exchange_boundary + apply_BCs_v4 (or v2) for one shape, from the flat tables */
+/* exchange_boundary + apply_BCs_v4 (or v2) for one shape, from the flat tables: copies and BC columns are
+ * independent of each other (FillBC::src), so this is a single phase */
 __device__ static void c_fill_ghosts(const CoarseLevel &V, const int id, const bool box_shape, const bool force_v2)
 {
   const DLevel &L = V.L;
+  double *v = L.base + (size_t)id * (size_t)L.volume;
   const int w = box_shape ? 1 : 0;
-  const CopyItem *xc = V.xch[w];
-  for (int e = threadIdx.x; e < V.n_xch[w]; e += blockDim.x) {
-    const CopyItem c = xc[e];
-    L.vec(c.wbox, id)[c.wcell] = L.vec(c.rbox, id)[c.rcell];
-  }
-  __syncthreads();
   const bool v2 = force_v2 || L.dim < 4;
-  if (v2) {                                                       /* boundary_fv.c:139-145: zero the regions first */
-    const ZeroItem *z = V.bcz[w];
-    for (int e = threadIdx.x; e < V.n_bcz[w]; e += blockDim.x) L.vec(z[e].box, id)[z[e].cell] = 0.0;
-    __syncthreads();
-  }
-  const BCItem *bc = V.bc[w];
-  for (int e = threadIdx.x; e < V.n_bc[w]; e += blockDim.x) {
-    const BCItem it = bc[e];
-    const BCNormal N = bc_normal(it.subtype, L.jStride, L.kStride);
-    double *x = L.vec(it.box, id);
-    if (v2) bc_v2_col(x, it.ijk, N.m, N.d[0], N.d[1], N.d[2]);
-    else    bc_v4_column(x, it.ijk, N);
+  const int ncopies = V.n_xch[w], work = ncopies + V.n_bc[w];
+  for (int e = threadIdx.x; e < work; e += blockDim.x) {
+    if (e < ncopies) {
+      const FillCopy c = V.xch[w][e];
+      v[c.dst] = v[c.src];
+    } else {
+      const FillBC it = V.bc[w][e - ncopies];
+      const BCNormal N = bc_normal(it.subtype, L.jStride, L.kStride);
+      if (v2) bc_v2_col_zero_rest(v + it.src, v + it.dst, N.m, N.d[0], N.d[1], N.d[2]);
+      else    bc_v4_column(v + it.src, v + it.dst, N);
+    }
   }
   __syncthreads();
 }
@@ -207,7 +201,7 @@ __device__ static void c_bottom_solve(const CoarseArgs &A, double *prod, double 
 {
   const CoarseLevel &V = A.lv[A.nlevels - 1];
   BottomArgs B;
-  B.L = V.L;  B.bc = V.bc[0];  B.nbc = V.n_bc[0];  B.bcz = V.bcz[0];  B.nbcz = V.n_bcz[0];
+  B.L = V.L;  B.bc = V.bc[0];  B.nbc = V.n_bc[0];
   B.x_id = A.e_id;  B.R_id = A.R_id;  B.a = A.a;  B.b = A.b;  B.h2inv = V.h2inv;  B.rtol = A.rtol;  B.iters = A.krylov;
   bicgstab_solve(B, prod, red);
   __syncthreads();
@@ -307,6 +301,7 @@ static int level_is_coarse_eligible(const level_type *level, int is_top, int is_
 {
   if (level->num_my_boxes != level->boxes_in.i * level->boxes_in.j * level->boxes_in.k) return 0;   /* every box of the level is mine */
   if (level->boundary_condition.type != BC_DIRICHLET || level->must_subtract_mean == 1) return 0;
+  if (HPGMG_DEV(level)->fill_nvec != level->numVectors) return 0;
   if ((long)level->dim.i * level->dim.j * level->dim.k > g_coarse_max_cells) return 0;
   for (int s = 0; s < STENCIL_MAX_SHAPES; s++)
     if (level->exchange_ghosts[s].num_sends || level->exchange_ghosts[s].num_recvs) return 0;
@@ -353,9 +348,8 @@ extern "C" void hpgmg_coarse_cycle(mg_type *MG, int from, int mode_ftail, int ze
     V.L = D->L;  V.low = D->low;
     const int shapes[2] = { STENCIL_SHAPE_NO_CORNERS, STENCIL_SHAPE_BOX };
     for (int w = 0; w < 2; w++) {
-      V.xch[w] = (const CopyItem *)D->copy_tab[shapes[w]].items;    V.n_xch[w] = D->copy_tab[shapes[w]].n;
-      V.bc[w] = (const BCItem *)D->bc_tab[shapes[w]].items;         V.n_bc[w] = D->bc_tab[shapes[w]].n;
-      V.bcz[w] = (const ZeroItem *)D->bczero_tab[shapes[w]].items;  V.n_bcz[w] = D->bczero_tab[shapes[w]].n;
+      V.xch[w] = D->fill[shapes[w]].copies;  V.n_xch[w] = D->fill[shapes[w]].ncopies;
+      V.bc[w] = D->fill[shapes[w]].bc;       V.n_bc[w] = D->fill[shapes[w]].nbc;
     }
     V.restr = D->restriction[RESTRICT_CELL][1].blocks;           V.n_restr = D->restriction[RESTRICT_CELL][1].n;
     V.interp = D->interpolation[1].blocks;                       V.n_interp = D->interpolation[1].n;

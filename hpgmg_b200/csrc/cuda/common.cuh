@@ -54,14 +54,21 @@ struct DList {
   int n;
 };
 
-/* Flat work tables of the small levels (<= COARSE_MAX_CELLS cells): the block lists expanded on the
- * host into one record per ghost cell / BC column, so that a single thread block can spread the work
- * over its threads without walking list entries one after the other (coarse.cu). */
+/* Flat work tables of a level's ghost fill (built on the host from the reference-identical block lists,
+ * device_level.cu): one record per ghost cell copied inside this GPU and one per BC column.  Offsets
+ * are in doubles from (DLevel::base + id*volume), i.e. they already contain box and cell.
+ * A BC column whose tangential coordinates lie in a ghost region reads the image of that region in the
+ * LOCAL neighbour box (src != dst), so copies and BCs have no mutual dependency and run as one kernel;
+ * columns that depend on a box owned by another GPU are "late": they read the box's own ghost cells
+ * after the unpack. */
 #define COARSE_MAX_CELLS 4096
-struct CopyItem { int rbox, rcell, wbox, wcell; };      /* cell offsets relative to cell (0,0,0) of a box vector */
-struct BCItem   { int box, subtype, ijk, pad; };        /* one BC column: nearest ghost cell + domain normal     */
-struct ZeroItem { int box, cell; };
-struct DTable   { void *items; int n; };
+struct FillCopy { int src, dst; };
+struct FillBC   { int dst, src, subtype, pad; };
+struct FillTable {
+  FillCopy *copies;  int ncopies;
+  FillBC   *bc;      int nbc;         /* local-source columns */
+  FillBC   *late;    int nlate;       /* columns that need data from another GPU first */
+};
 
 /* device mirror hanging off level_type::fluxes */
 struct hpgmg_device_level {
@@ -71,7 +78,8 @@ struct hpgmg_device_level {
   DList  exchange[STENCIL_MAX_SHAPES][3];
   DList  restriction[4][3];
   DList  interpolation[3];
-  DTable copy_tab[STENCIL_MAX_SHAPES], bc_tab[STENCIL_MAX_SHAPES], bczero_tab[STENCIL_MAX_SHAPES];   /* small levels only */
+  FillTable fill[STENCIL_MAX_SHAPES];
+  int fill_nvec;                                /* numVectors the fill offsets were built for */
   double *tile_partials;                        /* scratch for dot/mean: one double per compute tile */
   blockCopy_type *tiles;                        /* device copy of level->my_blocks                  */
   int     ntiles;

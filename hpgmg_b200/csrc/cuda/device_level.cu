@@ -25,54 +25,100 @@ static void free_list(DList *l)
   l->n = 0;
 }
 
-static void upload_table(DTable *t, const void *host, int n, size_t item)
+template <class T>
+static T *upload_items(const std::vector<T> &v)
 {
-  t->items = NULL;
-  t->n = n;
-  if (n <= 0) return;
-  CUDA_CHECK(cudaMalloc(&t->items, (size_t)n * item));
-  CUDA_CHECK(cudaMemcpyAsync(t->items, host, (size_t)n * item, cudaMemcpyHostToDevice, g_stream));
+  if (v.empty()) return NULL;
+  T *d = NULL;
+  CUDA_CHECK(cudaMalloc(&d, v.size() * sizeof(T)));
+  CUDA_CHECK(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, g_stream));
   CUDA_CHECK(cudaStreamSynchronize(g_stream));
+  return d;
 }
 
-/* expand the local ghost-exchange list and the BC list of every shape into per-cell / per-column records */
-static void build_small_level_tables(level_type *level, hpgmg_device_level *D)
+static void free_fill_tables(hpgmg_device_level *D)
 {
-  const int jS = level->box_jStride, kS = level->box_kStride, n = level->box_dim;
   for (int s = 0; s < STENCIL_MAX_SHAPES; s++) {
-    std::vector<CopyItem> copies;
+    FillTable &T = D->fill[s];
+    if (T.copies) CUDA_CHECK(cudaFree(T.copies));
+    if (T.bc) CUDA_CHECK(cudaFree(T.bc));
+    if (T.late) CUDA_CHECK(cudaFree(T.late));
+    memset(&T, 0, sizeof(T));
+  }
+}
+
+/* Expand the local ghost-exchange list and the BC list of every shape into per-cell / per-column records
+ * (see FillTable in common.cuh).  The lists themselves are the reference's (level.c:367-465, 498-922);
+ * this only flattens them and resolves, for each BC column, where its interior values come from. */
+static void build_fill_tables(level_type *level, hpgmg_device_level *D)
+{
+  free_fill_tables(D);
+  D->fill_nvec = level->numVectors;
+  if (level->num_my_boxes == 0 || level->box_ghosts != 2) return;
+  const int jS = level->box_jStride, kS = level->box_kStride, n = level->box_dim, g = level->box_ghosts;
+  const long per_box = (long)level->numVectors * level->box_volume;
+  const long origin = (long)g * (1 + jS + kS);
+  if (per_box * level->num_my_boxes >= 2147483647L) return;           /* offsets are 32-bit: fall back to the list kernels */
+  /* local index of every box I own, by global id */
+  const int total = level->boxes_in.i * level->boxes_in.j * level->boxes_in.k;
+  std::vector<int> local_of(total, -1);
+  for (int b = 0; b < level->num_my_boxes; b++) local_of[level->my_boxes[b].global_box_id] = b;
+
+  for (int s = 0; s < STENCIL_MAX_SHAPES; s++) {
+    std::vector<FillCopy> copies;
     const blockCopy_type *xb = level->exchange_ghosts[s].blocks[1];
     for (int e = 0; e < level->exchange_ghosts[s].num_blocks[1]; e++) {
       const blockCopy_type &B = xb[e];
+      const long rb = B.read.box * per_box + origin, wb = B.write.box * per_box + origin;
       for (int k = 0; k < B.dim.k; k++) for (int j = 0; j < B.dim.j; j++) for (int i = 0; i < B.dim.i; i++) {
-        CopyItem c = { B.read.box, (B.read.i + i) + (B.read.j + j) * jS + (B.read.k + k) * kS,
-                       B.write.box, (B.write.i + i) + (B.write.j + j) * jS + (B.write.k + k) * kS };
+        FillCopy c = { (int)(rb + (B.read.i + i) + (long)(B.read.j + j) * jS + (long)(B.read.k + k) * kS),
+                       (int)(wb + (B.write.i + i) + (long)(B.write.j + j) * jS + (long)(B.write.k + k) * kS) };
         copies.push_back(c);
       }
     }
-    std::vector<BCItem> cols;
-    std::vector<ZeroItem> zeros;
+    std::vector<FillBC> now, late;
     const blockCopy_type *bb = level->boundary_condition.blocks[s];
     for (int e = 0; e < level->boundary_condition.num_blocks[s]; e++) {
       const blockCopy_type &B = bb[e];
       const int nrm[3] = { (B.subtype % 3) - 1, ((B.subtype % 9) / 3) - 1, (B.subtype / 9) - 1 };
-      const int lo[3] = { B.read.i, B.read.j, B.read.k }, ext[3] = { B.dim.i, B.dim.j, B.dim.k }, st[3] = { 1, jS, kS };
-      for (int k = 0; k < ext[2]; k++) for (int j = 0; j < ext[1]; j++) for (int i = 0; i < ext[0]; i++) {
-        ZeroItem z = { B.read.box, (lo[0] + i) + (lo[1] + j) * jS + (lo[2] + k) * kS };
-        zeros.push_back(z);
-      }
+      const int lo[3] = { B.read.i, B.read.j, B.read.k }, ext[3] = { B.dim.i, B.dim.j, B.dim.k };
+      const long st[3] = { 1, jS, kS };
+      const box_type &box = level->my_boxes[B.read.box];
+      const int bc[3] = { box.low.i / n, box.low.j / n, box.low.k / n };
       const int e0 = nrm[0] ? 1 : ext[0], e1 = nrm[1] ? 1 : ext[1], e2 = nrm[2] ? 1 : ext[2];
       for (int c = 0; c < e0 * e1 * e2; c++) {
         const int p[3] = { c % e0, (c / e0) % e1, c / (e0 * e1) };
-        int ijk = 0;
-        for (int a = 0; a < 3; a++) ijk += (nrm[a] ? (nrm[a] < 0 ? -1 : n) : p[a] + lo[a]) * st[a];
-        BCItem it = { B.read.box, B.subtype, ijk, 0 };
-        cols.push_back(it);
+        long cell = 0, image = 0;
+        int nb[3] = { bc[0], bc[1], bc[2] }, shifted = 0;
+        for (int a = 0; a < 3; a++) {
+          if (nrm[a]) {                                   /* normal axis: nearest ghost cell, same in both frames */
+            const int t = nrm[a] < 0 ? -1 : n;
+            cell += t * st[a];  image += t * st[a];
+          } else {
+            const int q = p[a] + lo[a];                   /* tangential coordinate, possibly in a ghost range */
+            cell += q * st[a];
+            if (q < 0)       { nb[a] -= 1; image += (q + n) * st[a]; shifted = 1; }
+            else if (q >= n) { nb[a] += 1; image += (q - n) * st[a]; shifted = 1; }
+            else             image += q * st[a];
+          }
+        }
+        FillBC it;
+        it.dst = (int)(B.read.box * per_box + origin + cell);
+        it.src = it.dst;
+        it.subtype = B.subtype;
+        it.pad = 0;
+        if (!shifted) { now.push_back(it); continue; }
+        /* the region the column reads is filled by exchange_boundary from box nb (always inside the domain) */
+        const int gid = nb[0] + nb[1] * level->boxes_in.i + nb[2] * level->boxes_in.i * level->boxes_in.j;
+        const int lb = (nb[0] < 0 || nb[1] < 0 || nb[2] < 0 || nb[0] >= level->boxes_in.i || nb[1] >= level->boxes_in.j || nb[2] >= level->boxes_in.k) ? -1 : local_of[gid];
+        if (lb >= 0) { it.src = (int)(lb * per_box + origin + image); now.push_back(it); }
+        else late.push_back(it);                          /* owned by another GPU: read my own ghost cells after the unpack */
       }
     }
-    upload_table(&D->copy_tab[s], copies.data(), (int)copies.size(), sizeof(CopyItem));
-    upload_table(&D->bc_tab[s], cols.data(), (int)cols.size(), sizeof(BCItem));
-    upload_table(&D->bczero_tab[s], zeros.data(), (int)zeros.size(), sizeof(ZeroItem));
+    FillTable &T = D->fill[s];
+    T.copies = upload_items(copies);  T.ncopies = (int)copies.size();
+    T.bc = upload_items(now);         T.nbc = (int)now.size();
+    T.late = upload_items(late);      T.nlate = (int)late.size();
   }
 }
 
@@ -89,6 +135,7 @@ extern "C" void hpgmg_device_level_rebind_vectors(level_type *level)
   L.volume = level->box_volume;
   L.origin = level->box_ghosts * (1 + level->box_jStride + level->box_kStride);
   L.base = (level->num_my_boxes > 0) ? level->my_boxes[0].vectors[0] : NULL;
+  if (!hpgmg_rt_layout_only() && D->fill_nvec != 0 && D->fill_nvec != level->numVectors) build_fill_tables(level, D);   /* offsets contain numVectors */
 }
 
 extern "C" void hpgmg_device_level_create(level_type *level)
@@ -116,7 +163,7 @@ extern "C" void hpgmg_device_level_create(level_type *level)
     for (int p = 0; p < 3; p++)
       upload_list(&D->exchange[s][p], level->exchange_ghosts[s].blocks[p], level->exchange_ghosts[s].num_blocks[p]);
   }
-  if ((long)level->dim.i * level->dim.j * level->dim.k <= COARSE_MAX_CELLS) build_small_level_tables(level, D);
+  build_fill_tables(level, D);
   D->ntiles = level->num_my_blocks;
   if (D->ntiles > 0) {
     CUDA_CHECK(cudaMalloc(&D->tiles, (size_t)D->ntiles * sizeof(blockCopy_type)));
@@ -148,11 +195,7 @@ extern "C" void hpgmg_device_level_destroy(level_type *level)
   }
   for (int t = 0; t < 4; t++) for (int p = 0; p < 3; p++) free_list(&D->restriction[t][p]);
   for (int p = 0; p < 3; p++) free_list(&D->interpolation[p]);
-  for (int s = 0; s < STENCIL_MAX_SHAPES; s++) {
-    if (D->copy_tab[s].items) CUDA_CHECK(cudaFree(D->copy_tab[s].items));
-    if (D->bc_tab[s].items) CUDA_CHECK(cudaFree(D->bc_tab[s].items));
-    if (D->bczero_tab[s].items) CUDA_CHECK(cudaFree(D->bczero_tab[s].items));
-  }
+  free_fill_tables(D);
   if (D->low) CUDA_CHECK(cudaFree(D->low));
   if (D->tiles) CUDA_CHECK(cudaFree(D->tiles));
   if (D->tile_partials) CUDA_CHECK(cudaFree(D->tile_partials));

@@ -96,6 +96,58 @@ __global__ void bc_v1_kernel(const DLevel L, const int id, const blockCopy_type 
   }
 }
 
+/* ---- fused ghost fill: exchange_boundary + apply_BCs in ONE kernel ------------------------------- */
+/* Threads [0, ncopies) copy one ghost cell each from the neighbouring box on this GPU; threads
+ * [ncopies, ncopies+nbc) extrapolate one BC column each, reading interior values straight from the
+ * box that owns them (FillBC::src), which makes the two kinds of work independent.  version: 4
+ * quartic, 2 quadratic (also zeroes the deeper ghost layer, like the reference). */
+__global__ void __launch_bounds__(256) fill_ghosts_kernel(const DLevel L, const int id, const FillCopy *__restrict__ copies, const int ncopies,
+                                                          const FillBC *__restrict__ bc, const int nbc, const int version)
+{
+  double *v = L.base + (size_t)id * (size_t)L.volume;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < ncopies) {
+    const FillCopy c = copies[t];
+    v[c.dst] = v[c.src];
+  } else if (t < ncopies + nbc) {
+    const FillBC it = bc[t - ncopies];
+    const BCNormal N = bc_normal(it.subtype, L.jStride, L.kStride);
+    if (version == 4) bc_v4_column(v + it.src, v + it.dst, N);
+    else              bc_v2_col_zero_rest(v + it.src, v + it.dst, N.m, N.d[0], N.d[1], N.d[2]);
+  }
+}
+
+/* exchange_boundary(level,id,shape) followed by apply_BCs_v4 (bc_version 4; v2 below 4^3 like
+ * boundary_fv.c:269) or apply_BCs_v2 (bc_version 2).  Identical results to the two separate calls. */
+void hpgmg_fill_ghosts(level_type *level, int id, int shape, int bc_version)
+{
+  hpgmg_device_level *D = HPGMG_DEV(level);
+  const FillTable &T = D->fill[shape];
+  const bool dirichlet = level->boundary_condition.type == BC_DIRICHLET;
+  int version = bc_version;
+  if (version == 4 && level->box_dim < 4) version = 2;
+  const bool have_tables = D->fill_nvec == level->numVectors && level->box_ghosts == 2 && !(version == 2 && level->box_dim < 2);
+  if (!have_tables) {                                   /* unusual geometry: the list kernels */
+    exchange_boundary(level, id, shape);
+    if (bc_version == 4) apply_BCs_v4(level, id, shape); else apply_BCs_v2(level, id, shape);
+    return;
+  }
+  communicator_type *C = &level->exchange_ghosts[shape];
+  const bool remote = level->num_ranks > 1 && (C->num_sends > 0 || C->num_recvs > 0);
+  if (remote) {
+    hpgmg_run_copy_list(D->L, id, D->exchange[shape][0]);                 /* pack   */
+    hpgmg_comm_exchange(level, C, 0);                                      /* send / recv */
+  }
+  const int nbc = dirichlet ? T.nbc : 0;
+  const int work = T.ncopies + nbc;
+  if (work > 0) LAUNCH(fill_ghosts_kernel, (work + 255) / 256, 256, 0, D->L, id, T.copies, T.ncopies, T.bc, nbc, version);
+  if (remote) {
+    hpgmg_comm_exchange_wait(level, C);
+    hpgmg_run_copy_list(D->L, id, D->exchange[shape][2]);                 /* unpack */
+    if (dirichlet && T.nlate > 0) LAUNCH(fill_ghosts_kernel, (T.nlate + 255) / 256, 256, 0, D->L, id, (const FillCopy *)NULL, 0, T.late, T.nlate, version);
+  }
+}
+
 extern "C" void apply_BCs_v1(level_type *level, int x_id, int shape)
 {
   if (shape >= STENCIL_MAX_SHAPES) shape = STENCIL_SHAPE_BOX;

@@ -126,10 +126,10 @@ static void launch_stencil(level_type *level, StencilArgs &A)
 }
 
 /* ------------------------------------------------------------------------------------------ */
+void hpgmg_fill_ghosts(level_type *level, int id, int shape, int bc_version);   /* ghost.cu */
 static void fill_ghosts(level_type *level, int id)
 {
-  exchange_boundary(level, id, stencil_get_shape());
-  apply_BCs(level, id, stencil_get_shape());
+  hpgmg_fill_ghosts(level, id, STENCIL_SHAPE_NO_CORNERS, 4);    /* exchange_boundary + apply_BCs, fused */
 }
 
 extern "C" int stencil_get_radius(void) { return 2; }

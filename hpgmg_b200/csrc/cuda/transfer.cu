@@ -12,6 +12,7 @@
 #include "common.cuh"
 
 void hpgmg_run_copy_list(const DLevel &L, int id, const DList &list);   /* ghost.cu */
+void hpgmg_fill_ghosts(level_type *level, int id, int shape, int bc_version);
 
 /* ---- restriction ------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(128) restriction_kernel(const DLevel Lc, const int id_c, const DLevel Lf, const int id_f,
@@ -189,15 +190,13 @@ static void interpolation_driver(level_type *level_f, int id_f, double prescale_
 
 extern "C" void interpolation_v2(level_type *level_f, int id_f, double prescale_f, level_type *level_c, int id_c)
 {
-  exchange_boundary(level_c, id_c, STENCIL_SHAPE_BOX);
-  apply_BCs_v2(level_c, id_c, STENCIL_SHAPE_BOX);
+  hpgmg_fill_ghosts(level_c, id_c, STENCIL_SHAPE_BOX, 2);       /* exchange_boundary(BOX) + apply_BCs_v2(BOX), fused */
   interpolation_driver<3>(level_f, id_f, prescale_f, level_c, id_c);
 }
 
 extern "C" void interpolation_v4(level_type *level_f, int id_f, double prescale_f, level_type *level_c, int id_c)
 {
-  exchange_boundary(level_c, id_c, STENCIL_SHAPE_BOX);
-  apply_BCs_v4(level_c, id_c, STENCIL_SHAPE_BOX);
+  hpgmg_fill_ghosts(level_c, id_c, STENCIL_SHAPE_BOX, 4);       /* exchange_boundary(BOX) + apply_BCs_v4(BOX), fused */
   interpolation_driver<5>(level_f, id_f, prescale_f, level_c, id_c);
 }
 
