@@ -80,13 +80,16 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(const StencilArgs 
 
 static int g_force_generic = -1, g_kchunk_override = -1;
 
+static int g_tiled_async = 1;
+
 template <int OP, int TI, int TJ>
 static void launch_tiled(const StencilArgs &A)
 {
   typedef TileCfg<TI, TJ> C;
   static bool configured = false;
   if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(stencil_tiled_kernel<OP, TI, TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(stencil_tiled_kernel<OP, TI, TJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(stencil_tiled_kernel<OP, TI, TJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     configured = true;
   }
   const int n = A.L.dim;
@@ -98,7 +101,8 @@ static void launch_tiled(const StencilArgs &A)
   if (g_kchunk_override > 0) chunks = (n + g_kchunk_override - 1) / g_kchunk_override;
   const int kchunk = (n + chunks - 1) / chunks;
   dim3 grid(tiles, chunks, A.L.nboxes), block(TI / 2, TJ);
-  LAUNCH((stencil_tiled_kernel<OP, TI, TJ>), grid, block, C::SMEM, A, kchunk);
+  if (g_tiled_async) LAUNCH((stencil_tiled_kernel<OP, TI, TJ, true>), grid, block, C::SMEM, A, kchunk);
+  else               LAUNCH((stencil_tiled_kernel<OP, TI, TJ, false>), grid, block, C::SMEM, A, kchunk);
 }
 
 template <int OP>
@@ -113,6 +117,8 @@ static void launch_stencil(level_type *level, StencilArgs &A)
   if (g_force_generic < 0) {
     const char *e = getenv("HPGMG_B200_GENERIC_STENCIL");
     g_force_generic = (e && atoi(e)) ? 1 : 0;
+    const char *as = getenv("HPGMG_B200_TILED_ASYNC");
+    if (as) g_tiled_async = atoi(as);
     const char *kc = getenv("HPGMG_B200_KCHUNK");
     if (kc) g_kchunk_override = atoi(kc);
   }

@@ -66,6 +66,41 @@ __device__ __forceinline__ void plane_park(const double2 (&reg)[NPT], double *__
   }
 }
 
+/* asynchronous variant: 8-byte cp.async straight from global into the two parity halves (no register
+ * staging; completion is awaited with cp.async.wait_all right before the step's barrier) */
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
+{
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+/* per-thread prefetch items of one plane: global offset (doubles, from the tile origin) and shared offset
+ * (doubles, from the slot base) of the even cell; the odd cell is at +1 / +HW */
+template <int NT, int HW, int NE, int NPT>
+struct PlaneItems {
+  int goff[NPT], soff[NPT];
+  __device__ __forceinline__ void init(const int jS, const int tid)
+  {
+#pragma unroll
+    for (int n = 0; n < NPT; n++) {
+      const int e = tid + n * NT;
+      const int r = e / HW, q = e - r * HW;
+      goff[n] = (e < NE) ? r * jS + 2 * q : -1;
+      soff[n] = r * 2 * HW + q;
+    }
+  }
+  __device__ __forceinline__ void fetch_async(const double *__restrict__ src, double *__restrict__ dst) const
+  {
+#pragma unroll
+    for (int n = 0; n < NPT; n++)
+      if (goff[n] >= 0) {
+        cp_async8(dst + soff[n], src + goff[n]);
+        cp_async8(dst + soff[n] + HW, src + goff[n] + 1);
+      }
+  }
+};
+
 /* shared-memory loader: value of the array at offset (di,dj,dk) from the thread's active cell.
  * plane[dk - DK0] points at the ring slot of plane k+dk; `row` is the thread's row inside the tile of
  * this array; same/other are the in-row offsets of the cell's own parity half and of the other half. */
@@ -80,7 +115,7 @@ struct TileLoader {
   }
 };
 
-template <int OP, int TI, int TJ>
+template <int OP, int TI, int TJ, bool ASYNC>
 __global__ void __launch_bounds__((TI / 2) * TJ, 2) stencil_tiled_kernel(const StencilArgs A, const int kchunk)
 {
   typedef TileCfg<TI, TJ> C;
@@ -105,7 +140,10 @@ __global__ void __launch_bounds__((TI / 2) * TJ, 2) stencil_tiled_kernel(const S
   const double *gbj = L.vec(box, VECTOR_BETA_J) + (i0 - 2) + (j0 - 1) * jS;
   const double *gbk = L.vec(box, VECTOR_BETA_K) + (i0 - 2) + (j0 - 1) * jS;
 
-  double2 px[C::XN], pbi[C::BN], pbj[C::BN], pbk[C::BN];
+  double2 px[C::XN], pbi[C::BN], pbj[C::BN], pbk[C::BN];        /* register staging (synchronous variant only) */
+  PlaneItems<C::NT, C::HW, C::XE, C::XN> ix;
+  PlaneItems<C::NT, C::HW, C::BE, C::BN> ib;
+  if (ASYNC) { ix.init(jS, tid); ib.init(jS, tid); }
 
   /* prologue: x planes k0-2..k0+2, beta_i/j planes k0-1..k0+1, beta_k planes k0, k0+1 */
   for (int kk = k0 - 2; kk <= k0 + 2; kk++) {
@@ -135,11 +173,20 @@ __global__ void __launch_bounds__((TI / 2) * TJ, 2) stencil_tiled_kernel(const S
   for (int k = k0; k < k1; k++) {
     /* ---- issue the loads of the next planes and of this plane's point-wise operands ---- */
     const bool more_x = (k + 3 <= k1 + 1), more_b = (k + 2 <= k1);
-    if (more_x) plane_fetch<C::NT, C::HW, C::XE, C::XN>(px, gx + (k + 3) * kS, jS, tid);
-    if (more_b) {
-      plane_fetch<C::NT, C::HW, C::BE, C::BN>(pbi, gbi + (k + 2) * kS, jS, tid);
-      plane_fetch<C::NT, C::HW, C::BE, C::BN>(pbj, gbj + (k + 2) * kS, jS, tid);
-      plane_fetch<C::NT, C::HW, C::BE, C::BN>(pbk, gbk + (k + 2) * kS, jS, tid);
+    if (ASYNC) {                                      /* straight into the spare ring slots, no registers */
+      if (more_x) ix.fetch_async(gx + (k + 3) * kS, xs + ((k + 5) % C::XP) * C::XPL);
+      if (more_b) {
+        ib.fetch_async(gbi + (k + 2) * kS, bis + ((k + 3) % C::BP) * C::BPL);
+        ib.fetch_async(gbj + (k + 2) * kS, bjs + ((k + 3) % C::BP) * C::BPL);
+        ib.fetch_async(gbk + (k + 2) * kS, bks + ((k + 2) % C::KP) * C::BPL);
+      }
+    } else {
+      if (more_x) plane_fetch<C::NT, C::HW, C::XE, C::XN>(px, gx + (k + 3) * kS, jS, tid);
+      if (more_b) {
+        plane_fetch<C::NT, C::HW, C::BE, C::BN>(pbi, gbi + (k + 2) * kS, jS, tid);
+        plane_fetch<C::NT, C::HW, C::BE, C::BN>(pbj, gbj + (k + 2) * kS, jS, tid);
+        plane_fetch<C::NT, C::HW, C::BE, C::BN>(pbk, gbk + (k + 2) * kS, jS, tid);
+      }
     }
     double2 rhs2 = make_double2(0.0, 0.0), dinv2 = make_double2(0.0, 0.0), xm2 = make_double2(0.0, 0.0);
     if (OP != OP_APPLY) rhs2 = *reinterpret_cast<const double2 *>(g_rhs + k * kS);
@@ -187,11 +234,15 @@ __global__ void __launch_bounds__((TI / 2) * TJ, 2) stencil_tiled_kernel(const S
     *reinterpret_cast<double2 *>(g_out + k * kS) = out2;
 
     /* ---- park the prefetched planes in the spare ring slots (nobody reads them during this step) ---- */
-    if (more_x) plane_park<C::NT, C::HW, C::XE, C::XN>(px, xs + ((k + 5) % C::XP) * C::XPL, tid);
-    if (more_b) {
-      plane_park<C::NT, C::HW, C::BE, C::BN>(pbi, bis + ((k + 3) % C::BP) * C::BPL, tid);
-      plane_park<C::NT, C::HW, C::BE, C::BN>(pbj, bjs + ((k + 3) % C::BP) * C::BPL, tid);
-      plane_park<C::NT, C::HW, C::BE, C::BN>(pbk, bks + ((k + 2) % C::KP) * C::BPL, tid);
+    if (ASYNC) {
+      cp_async_wait_all();
+    } else {
+      if (more_x) plane_park<C::NT, C::HW, C::XE, C::XN>(px, xs + ((k + 5) % C::XP) * C::XPL, tid);
+      if (more_b) {
+        plane_park<C::NT, C::HW, C::BE, C::BN>(pbi, bis + ((k + 3) % C::BP) * C::BPL, tid);
+        plane_park<C::NT, C::HW, C::BE, C::BN>(pbj, bjs + ((k + 3) % C::BP) * C::BPL, tid);
+        plane_park<C::NT, C::HW, C::BE, C::BN>(pbk, bks + ((k + 2) % C::KP) * C::BPL, tid);
+      }
     }
     __syncthreads();
   }
