@@ -35,6 +35,8 @@ struct NcclApi {
   const char *(*GetErrorString)(ncclResult_t);
 };
 static NcclApi N = {};
+static void p2p_setup(void);
+extern "C" void hpgmg_b200_p2p_finalize(void);
 static ncclComm_t g_comm = NULL;
 static int g_rank = 0, g_nranks = 1;
 static hpgmg_allgather_fn g_allgather = NULL;
@@ -80,10 +82,12 @@ extern "C" void hpgmg_b200_set_comm(int my_rank, int num_ranks, hpgmg_allgather_
   id = all[0];
   free(all);
   NCCL_CHECK(N.CommInitRank(&g_comm, num_ranks, id, my_rank));
+  p2p_setup();
 }
 
 extern "C" void hpgmg_b200_comm_finalize(void)
 {
+  hpgmg_b200_p2p_finalize();
   if (g_comm) { hpgmg_rt_sync(); N.CommDestroy(g_comm); g_comm = NULL; }
   g_nranks = 1;  g_rank = 0;
 }
@@ -158,3 +162,195 @@ extern "C" void hpgmg_comm_transfer(level_type *level_send, communicator_type *C
 }
 extern "C" void hpgmg_comm_transfer_wait(level_type *level_send, communicator_type *Cs, level_type *level_recv, communicator_type *Cr)
 { (void)level_send; (void)Cs; (void)level_recv; (void)Cr; /* stream-ordered */ }
+
+/* ================================================================================================
+ * Direct peer-to-peer ghost exchange over NVLink (replaces the ncclSend/ncclRecv pair, whose ~20 us
+ * of launch latency per message group dominates a multigrid cycle made of ~400 tiny exchanges).
+ *
+ * Every rank owns one "comm arena" of device memory, exported once with CUDA IPC and mapped by all
+ * peers.  Receive buffers of the ghost exchange and two flags per neighbour live in it:
+ *   - the SENDER's pack kernel copies its faces/edges/corners straight into the RECEIVER's buffer
+ *     (NVLink stores, no staging copy, no NCCL) and then publishes the message by writing the
+ *     exchange's sequence number into the receiver's DATA flag (system-scope release);
+ *   - the receiver's unpack kernel spins on that flag (acquire), copies buffer -> ghost cells and
+ *     acknowledges by writing the sequence number into the sender's ACK flag; the sender's next pack
+ *     waits for that ACK before it overwrites the buffer (normally long since satisfied).
+ * Sequence numbers live in device memory and are advanced by the kernels themselves, so the whole
+ * thing is capturable in the solve's CUDA graph; the host never waits.  Order of messages and buffer
+ * layout are the reference's (level.c:79-92, 724, 878).
+ * ================================================================================================ */
+#include <map>
+#include <vector>
+
+#include "p2p.cuh"
+
+struct P2PHost {
+  P2PPlan *plan;                                   /* device */
+  blockCopy_type *pack, *unpack;                   /* device copies: write.ptr -> remote buffers; subtype = neighbour index */
+  int npack, nunpack;
+};
+
+static char *g_arena = NULL;
+static size_t g_arena_size = 0, g_arena_used = 0;
+static std::vector<char *> g_peer_arena;          /* my mapping of every rank's arena */
+static std::map<communicator_type *, P2PHost> g_p2p;
+static int g_p2p_enabled = 0;
+
+extern "C" int hpgmg_rt_is_comm_memory(const void *p) { return g_arena && (const char *)p >= g_arena && (const char *)p < g_arena + g_arena_size; }
+
+extern "C" void *hpgmg_rt_alloc_comm(size_t bytes)
+{
+  if (!g_arena) return hpgmg_rt_alloc_zero(bytes);
+  const size_t need = (bytes + 255) & ~(size_t)255;
+  if (g_arena_used + need > g_arena_size) {
+    fprintf(stderr, "hpgmg_b200: comm arena exhausted (%zu of %zu bytes used, %zu requested); set HPGMG_B200_COMM_ARENA_MB\n", g_arena_used, g_arena_size, bytes);
+    exit(1);
+  }
+  void *p = g_arena + g_arena_used;               /* never reused, and the arena was zeroed (synchronously) when it was created:
+                                                     a stream-ordered memset here could run AFTER a fast peer's first store */
+  g_arena_used += need;
+  return p;
+}
+
+/* called from hpgmg_b200_set_comm once NCCL is up: create, export and map the arenas */
+static void p2p_setup(void)
+{
+  const char *off = getenv("HPGMG_B200_NO_P2P");
+  if (off && atoi(off)) return;
+  const char *mb = getenv("HPGMG_B200_COMM_ARENA_MB");
+  g_arena_size = (size_t)(mb ? atol(mb) : 512) << 20;
+  if (cudaMalloc((void **)&g_arena, g_arena_size) != cudaSuccess) { cudaGetLastError(); g_arena = NULL; return; }
+  CUDA_CHECK(cudaMemset(g_arena, 0, g_arena_size));
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, g_arena) != cudaSuccess) { cudaGetLastError(); fprintf(stderr, "hpgmg_b200: CUDA IPC export failed; falling back to NCCL send/recv\n"); cudaFree(g_arena); g_arena = NULL; return; }
+  std::vector<cudaIpcMemHandle_t> all((size_t)g_nranks);
+  g_allgather(&mine, all.data(), sizeof(mine), g_comm_ctx);
+  g_peer_arena.assign((size_t)g_nranks, (char *)NULL);
+  int ok = 1;
+  for (int r = 0; r < g_nranks; r++) {
+    if (r == g_rank) { g_peer_arena[r] = g_arena; continue; }
+    void *p = NULL;
+    if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+    g_peer_arena[r] = (char *)p;
+  }
+  /* everybody must agree, otherwise the protocol deadlocks */
+  std::vector<int> oks((size_t)g_nranks);
+  g_allgather(&ok, oks.data(), sizeof(int), g_comm_ctx);
+  for (int r = 0; r < g_nranks; r++) ok &= oks[r];
+  if (!ok) { if (g_rank == 0) fprintf(stderr, "hpgmg_b200: CUDA IPC peer mapping unavailable; using NCCL send/recv for halos\n"); g_p2p_enabled = 0; return; }
+  g_p2p_enabled = 1;
+}
+
+struct P2PWire {                                   /* what a rank tells the others about one communicator */
+  int nrecv, nsend;
+  int recv_from[P2P_MAX_NEIGHBOURS];  long long recv_buf_off[P2P_MAX_NEIGHBOURS], data_flag_off[P2P_MAX_NEIGHBOURS];
+  int send_to[P2P_MAX_NEIGHBOURS];    long long ack_flag_off[P2P_MAX_NEIGHBOURS];
+};
+
+extern "C" void hpgmg_comm_register_exchange(level_type *level, int shape)
+{
+  if (!g_p2p_enabled || g_nranks <= 1 || hpgmg_rt_layout_only()) return;
+  communicator_type *C = &level->exchange_ghosts[shape];
+  P2PWire mine;
+  memset(&mine, 0, sizeof(mine));
+  int fits = (C->num_recvs <= P2P_MAX_NEIGHBOURS && C->num_sends <= P2P_MAX_NEIGHBOURS);
+  unsigned long long *flags = NULL;
+  if (fits && (C->num_recvs + C->num_sends) > 0) flags = (unsigned long long *)hpgmg_rt_alloc_comm(sizeof(unsigned long long) * (size_t)(C->num_recvs + C->num_sends));
+  if (fits) {
+    mine.nrecv = C->num_recvs;  mine.nsend = C->num_sends;
+    for (int n = 0; n < C->num_recvs; n++) {
+      mine.recv_from[n] = C->recv_ranks[n];
+      mine.recv_buf_off[n] = hpgmg_rt_is_comm_memory(C->recv_buffers[n]) ? (long long)((char *)C->recv_buffers[n] - g_arena) : -1;
+      mine.data_flag_off[n] = (long long)((char *)(flags + n) - g_arena);
+    }
+    for (int n = 0; n < C->num_sends; n++) {
+      mine.send_to[n] = C->send_ranks[n];
+      mine.ack_flag_off[n] = (long long)((char *)(flags + C->num_recvs + n) - g_arena);
+    }
+  } else mine.nrecv = mine.nsend = -1;
+  std::vector<P2PWire> all((size_t)g_nranks);
+  g_allgather(&mine, all.data(), sizeof(P2PWire), g_comm_ctx);
+  for (int r = 0; r < g_nranks; r++) if (all[r].nrecv < 0) return;            /* somebody cannot: everybody keeps NCCL for this one */
+  if (C->num_recvs + C->num_sends == 0) return;
+
+  P2PPlan h;
+  memset(&h, 0, sizeof(h));
+  std::vector<double *> remote_buf((size_t)C->num_sends, (double *)NULL);
+  for (int n = 0; n < C->num_sends; n++) {
+    const int R = C->send_ranks[n];
+    int found = -1;
+    for (int m = 0; m < all[R].nrecv; m++) if (all[R].recv_from[m] == g_rank) found = m;
+    if (found < 0 || all[R].recv_buf_off[found] < 0) { fprintf(stderr, "hpgmg_b200: rank %d has no receive buffer for rank %d\n", R, g_rank); exit(1); }
+    remote_buf[n] = (double *)(g_peer_arena[R] + all[R].recv_buf_off[found]);
+    h.remote_data_flag[n] = (unsigned long long *)(g_peer_arena[R] + all[R].data_flag_off[found]);
+    h.local_ack_flag[n] = flags + C->num_recvs + n;
+  }
+  for (int n = 0; n < C->num_recvs; n++) {
+    const int S = C->recv_ranks[n];
+    int found = -1;
+    for (int m = 0; m < all[S].nsend; m++) if (all[S].send_to[m] == g_rank) found = m;
+    if (found < 0) { fprintf(stderr, "hpgmg_b200: rank %d does not send to rank %d\n", S, g_rank); exit(1); }
+    h.local_data_flag[n] = flags + n;
+    h.remote_ack_flag[n] = (unsigned long long *)(g_peer_arena[S] + all[S].ack_flag_off[found]);
+  }
+  /* device copies of the pack / unpack lists: pack writes go to the REMOTE buffers; subtype = neighbour */
+  P2PHost H;
+  memset(&H, 0, sizeof(H));
+  std::vector<blockCopy_type> pack(C->blocks[0], C->blocks[0] + C->num_blocks[0]), unpack(C->blocks[2], C->blocks[2] + C->num_blocks[2]);
+  for (size_t e = 0; e < pack.size(); e++) {
+    int n = -1;
+    for (int m = 0; m < C->num_sends; m++) if (pack[e].write.ptr == C->send_buffers[m]) n = m;
+    if (n < 0) { fprintf(stderr, "hpgmg_b200: pack entry without a send buffer\n"); exit(1); }
+    pack[e].write.ptr = remote_buf[n];
+    pack[e].subtype = n;
+    h.send_blocks[n]++;
+  }
+  for (size_t e = 0; e < unpack.size(); e++) {
+    int n = -1;
+    for (int m = 0; m < C->num_recvs; m++) if (unpack[e].read.ptr == C->recv_buffers[m]) n = m;
+    if (n < 0) { fprintf(stderr, "hpgmg_b200: unpack entry without a receive buffer\n"); exit(1); }
+    unpack[e].subtype = n;
+    h.recv_blocks[n]++;
+  }
+  H.npack = (int)pack.size();  H.nunpack = (int)unpack.size();
+  if (H.npack) { CUDA_CHECK(cudaMalloc(&H.pack, pack.size() * sizeof(blockCopy_type))); CUDA_CHECK(cudaMemcpy(H.pack, pack.data(), pack.size() * sizeof(blockCopy_type), cudaMemcpyHostToDevice)); }
+  if (H.nunpack) { CUDA_CHECK(cudaMalloc(&H.unpack, unpack.size() * sizeof(blockCopy_type))); CUDA_CHECK(cudaMemcpy(H.unpack, unpack.data(), unpack.size() * sizeof(blockCopy_type), cudaMemcpyHostToDevice)); }
+  CUDA_CHECK(cudaMalloc(&H.plan, sizeof(P2PPlan)));
+  CUDA_CHECK(cudaMemcpy(H.plan, &h, sizeof(P2PPlan), cudaMemcpyHostToDevice));
+  g_p2p[C] = H;
+}
+
+extern "C" void hpgmg_comm_unregister(communicator_type *C)
+{
+  std::map<communicator_type *, P2PHost>::iterator it = g_p2p.find(C);
+  if (it == g_p2p.end()) return;
+  hpgmg_rt_sync();
+  if (it->second.pack) cudaFree(it->second.pack);
+  if (it->second.unpack) cudaFree(it->second.unpack);
+  cudaFree(it->second.plan);
+  g_p2p.erase(it);
+}
+
+/* hand the peer-exchange state of a communicator to the kernels in ghost.cu; 0 if it is not on the peer path */
+int hpgmg_comm_p2p_lookup(level_type *level, int shape, const blockCopy_type **pack, int *npack, const blockCopy_type **unpack, int *nunpack, P2PPlan **plan)
+{
+  if (!g_p2p_enabled) return 0;
+  std::map<communicator_type *, P2PHost>::iterator it = g_p2p.find(&level->exchange_ghosts[shape]);
+  if (it == g_p2p.end()) return 0;
+  *pack = it->second.pack;      *npack = it->second.npack;
+  *unpack = it->second.unpack;  *nunpack = it->second.nunpack;
+  *plan = it->second.plan;
+  return 1;
+}
+
+extern "C" void hpgmg_b200_p2p_finalize(void)
+{
+  if (!g_arena) return;
+  hpgmg_rt_sync();
+  for (int r = 0; r < (int)g_peer_arena.size(); r++) if (r != g_rank && g_peer_arena[r]) cudaIpcCloseMemHandle(g_peer_arena[r]);
+  g_peer_arena.clear();
+  if (g_barrier) g_barrier(g_comm_ctx);             /* nobody frees while a peer may still have it mapped */
+  cudaFree(g_arena);
+  g_arena = NULL;  g_arena_size = g_arena_used = 0;  g_p2p_enabled = 0;
+}
+extern "C" int hpgmg_b200_p2p_enabled(void) { return g_p2p_enabled; }

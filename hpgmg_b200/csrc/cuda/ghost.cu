@@ -15,6 +15,7 @@
  * bit-identical.
  */
 #include "common.cuh"
+#include "p2p.cuh"
 
 /* ---- copy lists ------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(128) copy_blocks_kernel(const DLevel L, const int id, const blockCopy_type *__restrict__ blocks)
@@ -42,15 +43,26 @@ void hpgmg_run_copy_list(const DLevel &L, int id, const DList &list)
   LAUNCH(copy_blocks_kernel, list.n, 128, 0, L, id, list.blocks);
 }
 
+void hpgmg_fill_ghosts(level_type *level, int id, int shape, int bc_version);
+
 extern "C" void exchange_boundary(level_type *level, int id, int shape)
 {
   if (shape >= STENCIL_MAX_SHAPES) shape = STENCIL_SHAPE_BOX;
   hpgmg_device_level *D = HPGMG_DEV(level);
-  if (level->num_ranks > 1 && (level->exchange_ghosts[shape].num_sends > 0 || level->exchange_ghosts[shape].num_recvs > 0)) {
+  communicator_type *C = &level->exchange_ghosts[shape];
+  const bool remote = level->num_ranks > 1 && (C->num_sends > 0 || C->num_recvs > 0);
+  if (remote) {
+    const blockCopy_type *pack, *unpack;
+    int npack, nunpack;
+    P2PPlan *plan;
+    if (D->fill_nvec == level->numVectors && level->box_ghosts == 2 && hpgmg_comm_p2p_lookup(level, shape, &pack, &npack, &unpack, &nunpack, &plan)) {
+      hpgmg_fill_ghosts(level, id, shape, 0);                              /* peer stores over NVLink, no BCs */
+      return;
+    }
     hpgmg_run_copy_list(D->L, id, D->exchange[shape][0]);                 /* pack   */
-    hpgmg_comm_exchange(level, &level->exchange_ghosts[shape], 0);         /* send / recv */
+    hpgmg_comm_exchange(level, C, 0);                                      /* ncclSend / ncclRecv */
     hpgmg_run_copy_list(D->L, id, D->exchange[shape][1]);                 /* local  */
-    hpgmg_comm_exchange_wait(level, &level->exchange_ghosts[shape]);
+    hpgmg_comm_exchange_wait(level, C);
     hpgmg_run_copy_list(D->L, id, D->exchange[shape][2]);                 /* unpack */
   } else {
     hpgmg_run_copy_list(D->L, id, D->exchange[shape][1]);
@@ -59,6 +71,7 @@ extern "C" void exchange_boundary(level_type *level, int id, int shape)
 
 /* ---- boundary conditions (device bodies in bc.cuh) ---------------------------------------------- */
 #include "bc.cuh"
+#include "p2p.cuh"
 
 __global__ void __launch_bounds__(128) bc_v4_kernel(const DLevel L, const int id, const blockCopy_type *__restrict__ blocks)
 {
@@ -96,16 +109,27 @@ __global__ void bc_v1_kernel(const DLevel L, const int id, const blockCopy_type 
   }
 }
 
-/* ---- fused ghost fill: exchange_boundary + apply_BCs in ONE kernel ------------------------------- */
-/* Threads [0, ncopies) copy one ghost cell each from the neighbouring box on this GPU; threads
- * [ncopies, ncopies+nbc) extrapolate one BC column each, reading interior values straight from the
- * box that owns them (FillBC::src), which makes the two kinds of work independent.  version: 4
- * quartic, 2 quadratic (also zeroes the deeper ghost layer, like the reference). */
-__global__ void __launch_bounds__(256) fill_ghosts_kernel(const DLevel L, const int id, const FillCopy *__restrict__ copies, const int ncopies,
-                                                          const FillBC *__restrict__ bc, const int nbc, const int version)
+/* ---- fused ghost fill: exchange_boundary + apply_BCs ---------------------------------------------- */
+/* One fill is at most TWO kernels:
+ *
+ *  send_fill_kernel   blocks [0, npack)  : one pack-list entry each -- copy box cells straight into the
+ *                                          neighbour GPU's receive buffer over NVLink, then publish the
+ *                                          message (p2p protocol, comm.cu);          [multi-GPU only]
+ *                     remaining blocks   : 256 work items each -- an item is either one ghost cell copied
+ *                                          from the neighbouring box on this GPU, or one BC column, which
+ *                                          reads its interior values straight from the box that owns them
+ *                                          (FillBC::src), so copies and BCs are independent.
+ *  recv_fill_kernel   blocks [0, nunpack): wait for the neighbour's message, copy buffer -> ghost cells,
+ *                                          acknowledge;                              [multi-GPU only]
+ *                     remaining blocks   : the BC columns that need those ghost cells; they wait (in-kernel
+ *                                          counter) until every unpack block of this launch has finished.
+ *                                          Blocks are dispatched in index order, so the unpack blocks are
+ *                                          always resident or finished before a waiting block exists.
+ * version: 4 quartic, 2 quadratic (also zeroes the deeper ghost layer, like the reference). */
+__device__ __forceinline__ void fill_items(const DLevel &L, const int id, const int t, const FillCopy *__restrict__ copies, const int ncopies,
+                                           const FillBC *__restrict__ bc, const int nbc, const int version)
 {
   double *v = L.base + (size_t)id * (size_t)L.volume;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < ncopies) {
     const FillCopy c = copies[t];
     v[c.dst] = v[c.src];
@@ -117,34 +141,127 @@ __global__ void __launch_bounds__(256) fill_ghosts_kernel(const DLevel L, const 
   }
 }
 
+__global__ void __launch_bounds__(256) send_fill_kernel(const DLevel L, const int id, const blockCopy_type *__restrict__ pack, const int npack, P2PPlan *plan,
+                                                        const FillCopy *__restrict__ copies, const int ncopies, const FillBC *__restrict__ bc, const int nbc, const int version)
+{
+  if ((int)blockIdx.x >= npack) {
+    fill_items(L, id, ((int)blockIdx.x - npack) * blockDim.x + threadIdx.x, copies, ncopies, bc, nbc, version);
+    return;
+  }
+  const blockCopy_type B = pack[blockIdx.x];
+  const int n = B.subtype;                                            /* neighbour index (set in comm.cu) */
+  __shared__ unsigned long long epoch_s;
+  if (threadIdx.x == 0) {
+    const unsigned long long epoch = *(volatile unsigned long long *)&plan->epoch_send;
+    while (ld_acquire_sys(plan->local_ack_flag[n]) < epoch) { }      /* the receiver has drained the previous message */
+    epoch_s = epoch;
+  }
+  __syncthreads();
+  const double *__restrict__ rd = L.vec(B.read.box, id) + B.read.i + B.read.j * L.jStride + B.read.k * L.kStride;
+  double *wr = B.write.ptr + B.write.i + B.write.j * B.write.jStride + B.write.k * B.write.kStride;
+  const int di = B.dim.i, dj = B.dim.j, cells = di * dj * B.dim.k;
+  for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+    const int i = c % di, j = (c / di) % dj, k = c / (di * dj);
+    wr[i + j * B.write.jStride + k * B.write.kStride] = rd[i + j * L.jStride + k * L.kStride];
+  }
+  __syncthreads();                                                    /* every thread's stores are ordered before thread 0's fence */
+  if (threadIdx.x == 0) {
+    const unsigned long long epoch = epoch_s;
+    __threadfence_system();
+    if (atomicAdd(&plan->send_count[n], 1u) == (unsigned)plan->send_blocks[n] - 1u) {   /* last entry for this neighbour */
+      plan->send_count[n] = 0;
+      __threadfence_system();
+      st_release_sys(plan->remote_data_flag[n], epoch + 1);
+    }
+    if (atomicAdd(&plan->done_send, 1u) == (unsigned)npack - 1u) {                        /* last pack block of the launch */
+      plan->done_send = 0;
+      __threadfence();
+      *(volatile unsigned long long *)&plan->epoch_send = epoch + 1;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) recv_fill_kernel(const DLevel L, const int id, const blockCopy_type *__restrict__ unpack, const int nunpack, P2PPlan *plan,
+                                                        const FillBC *__restrict__ late, const int nlate, const int nlate_blocks, const int version)
+{
+  if ((int)blockIdx.x >= nunpack) {                                   /* BC columns that read unpacked ghost cells */
+    if (threadIdx.x == 0) {
+      while (*(volatile unsigned int *)&plan->done_recv < (unsigned)nunpack) { }
+      __threadfence();
+    }
+    __syncthreads();
+    fill_items(L, id, ((int)blockIdx.x - nunpack) * blockDim.x + threadIdx.x, (const FillCopy *)nullptr, 0, late, nlate, version);
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(&plan->late_passed, 1u) == (unsigned)nlate_blocks - 1u) {
+      plan->late_passed = 0;
+      plan->done_recv = 0;                                            /* re-arm for the next launch */
+    }
+    return;
+  }
+  const blockCopy_type B = unpack[blockIdx.x];
+  const int n = B.subtype;
+  __shared__ unsigned long long epoch_s;
+  if (threadIdx.x == 0) {
+    const unsigned long long epoch = *(volatile unsigned long long *)&plan->epoch_recv;
+    while (ld_acquire_sys(plan->local_data_flag[n]) < epoch + 1) { }  /* the sender's stores have landed */
+    epoch_s = epoch;
+  }
+  __syncthreads();
+  const double *rd = B.read.ptr + B.read.i + B.read.j * B.read.jStride + B.read.k * B.read.kStride;
+  double *__restrict__ wr = L.vec(B.write.box, id) + B.write.i + B.write.j * L.jStride + B.write.k * L.kStride;
+  const int di = B.dim.i, dj = B.dim.j, cells = di * dj * B.dim.k;
+  for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+    const int i = c % di, j = (c / di) % dj, k = c / (di * dj);
+    wr[i + j * L.jStride + k * L.kStride] = __ldcv(rd + i + j * B.read.jStride + k * B.read.kStride);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long epoch = epoch_s;
+    __threadfence();
+    if (atomicAdd(&plan->recv_count[n], 1u) == (unsigned)plan->recv_blocks[n] - 1u) {
+      plan->recv_count[n] = 0;
+      __threadfence_system();
+      st_release_sys(plan->remote_ack_flag[n], epoch + 1);            /* the sender may reuse the buffer */
+    }
+    const unsigned int done = atomicAdd(&plan->done_recv, 1u);
+    if (done == (unsigned)nunpack - 1u) {                              /* last unpack block of the launch */
+      __threadfence();
+      *(volatile unsigned long long *)&plan->epoch_recv = epoch + 1;
+      if (nlate_blocks == 0) plan->done_recv = 0;                      /* nobody else will re-arm it */
+    }
+  }
+}
+
 /* exchange_boundary(level,id,shape) followed by apply_BCs_v4 (bc_version 4; v2 below 4^3 like
- * boundary_fv.c:269) or apply_BCs_v2 (bc_version 2).  Identical results to the two separate calls. */
+ * boundary_fv.c:269), apply_BCs_v2 (bc_version 2), or nothing (bc_version 0).  Identical results to the
+ * separate list-walking kernels. */
 void hpgmg_fill_ghosts(level_type *level, int id, int shape, int bc_version)
 {
   hpgmg_device_level *D = HPGMG_DEV(level);
   const FillTable &T = D->fill[shape];
-  const bool dirichlet = level->boundary_condition.type == BC_DIRICHLET;
+  const bool dirichlet = level->boundary_condition.type == BC_DIRICHLET && bc_version != 0;
   int version = bc_version;
   if (version == 4 && level->box_dim < 4) version = 2;
-  const bool have_tables = D->fill_nvec == level->numVectors && level->box_ghosts == 2 && !(version == 2 && level->box_dim < 2);
-  if (!have_tables) {                                   /* unusual geometry: the list kernels */
-    exchange_boundary(level, id, shape);
-    if (bc_version == 4) apply_BCs_v4(level, id, shape); else apply_BCs_v2(level, id, shape);
-    return;
-  }
   communicator_type *C = &level->exchange_ghosts[shape];
   const bool remote = level->num_ranks > 1 && (C->num_sends > 0 || C->num_recvs > 0);
-  if (remote) {
-    hpgmg_run_copy_list(D->L, id, D->exchange[shape][0]);                 /* pack   */
-    hpgmg_comm_exchange(level, C, 0);                                      /* send / recv */
+  const bool have_tables = D->fill_nvec == level->numVectors && level->box_ghosts == 2 && !(version == 2 && level->box_dim < 2);
+  const blockCopy_type *pack = NULL, *unpack = NULL;
+  int npack = 0, nunpack = 0;
+  P2PPlan *plan = NULL;
+  const int p2p = (remote && have_tables) ? hpgmg_comm_p2p_lookup(level, shape, &pack, &npack, &unpack, &nunpack, &plan) : 0;
+  if (!have_tables || (remote && !p2p)) {                /* unusual geometry, or no peer mapping: the list kernels (+ NCCL) */
+    exchange_boundary(level, id, shape);
+    if (bc_version == 4) apply_BCs_v4(level, id, shape); else if (bc_version == 2) apply_BCs_v2(level, id, shape);
+    return;
   }
-  const int nbc = dirichlet ? T.nbc : 0;
-  const int work = T.ncopies + nbc;
-  if (work > 0) LAUNCH(fill_ghosts_kernel, (work + 255) / 256, 256, 0, D->L, id, T.copies, T.ncopies, T.bc, nbc, version);
+  const int nbc = dirichlet ? T.nbc : 0, nlate = dirichlet ? T.nlate : 0;
+  const int fill_blocks = (T.ncopies + nbc + 255) / 256;
+  if (npack + fill_blocks > 0)
+    LAUNCH(send_fill_kernel, npack + fill_blocks, 256, 0, D->L, id, pack, npack, plan, T.copies, T.ncopies, T.bc, nbc, version);
   if (remote) {
-    hpgmg_comm_exchange_wait(level, C);
-    hpgmg_run_copy_list(D->L, id, D->exchange[shape][2]);                 /* unpack */
-    if (dirichlet && T.nlate > 0) LAUNCH(fill_ghosts_kernel, (T.nlate + 255) / 256, 256, 0, D->L, id, (const FillCopy *)NULL, 0, T.late, T.nlate, version);
+    const int late_blocks = (nlate + 255) / 256;
+    if (nunpack + late_blocks > 0)
+      LAUNCH(recv_fill_kernel, nunpack + late_blocks, 256, 0, D->L, id, unpack, nunpack, plan, T.late, nlate, late_blocks, version);
   }
 }
 

@@ -384,7 +384,7 @@ static void build_exchange_ghosts(level_type *L, int shape)
     total += (size_t)ei * ej * ek;
   }
   if (nRecvRanks > 0) {
-    double *bulk = (double *)MALLOC(total * sizeof(double));
+    double *bulk = (double *)hpgmg_rt_alloc_comm(total * sizeof(double));   /* peer-visible: neighbours store straight into it */
     for (int r = 0; r < nRecvRanks; r++) { C->recv_buffers[r] = bulk; bulk += C->recv_sizes[r]; }
   }
   cursor = (int *)calloc((size_t)(nRecvRanks > 0 ? nRecvRanks : 1), sizeof(int));
@@ -516,6 +516,7 @@ void create_level(level_type *L, int boxes_in_i, int box_dim, int box_ghosts, in
   }
 
   for (int shape = 0; shape < STENCIL_MAX_SHAPES; shape++) build_exchange_ghosts(L, shape);
+  for (int shape = 0; shape < STENCIL_MAX_SHAPES; shape++) hpgmg_comm_register_exchange(L, shape);   /* collective: swaps buffer/flag addresses */
   for (int shape = 0; shape < STENCIL_MAX_SHAPES; shape++) build_boundary_conditions(L, shape);
   for (int t = 0; t < 4; t++) reset_communicator(&L->restriction[t]);
   reset_communicator(&L->interpolation);
@@ -568,6 +569,6 @@ void destroy_level(level_type *L)
   free(L->my_boxes);
   free(L->my_blocks);
   for (int s = 0; s < STENCIL_MAX_SHAPES; s++) free(L->boundary_condition.blocks[s]);
-  for (int s = 0; s < STENCIL_MAX_SHAPES; s++) free_communicator(&L->exchange_ghosts[s]);
+  for (int s = 0; s < STENCIL_MAX_SHAPES; s++) { hpgmg_comm_unregister(&L->exchange_ghosts[s]); free_communicator(&L->exchange_ghosts[s]); }
   if (chatty) fprintf(stdout, "done\n");
 }

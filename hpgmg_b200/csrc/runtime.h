@@ -69,6 +69,12 @@ int  hpgmg_bicgstab_device(level_type *level, int x_id, int R_id, double a, doub
 
 void hpgmg_rt_zero_scalar(int slot);                  /* async, capturable */
 
+/* peer-visible device memory for receive buffers and flags (comm.cu); plain device memory on one rank */
+void  *hpgmg_rt_alloc_comm(size_t bytes);
+int    hpgmg_rt_is_comm_memory(const void *p);
+void   hpgmg_comm_register_exchange(level_type *level, int shape);   /* collective over all ranks */
+void   hpgmg_comm_unregister(communicator_type *C);
+
 /* inter-GPU plumbing (comm.cu): no-ops on a single rank */
 int    hpgmg_comm_rank(void);
 int    hpgmg_comm_size(void);

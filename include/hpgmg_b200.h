@@ -109,12 +109,15 @@ void   hpgmg_b200_gsrb_sweep(level_type *level, int src_id, int dst_id, int rhs_
  * Here ranks are processes launched by torchrun, one per GPU.  The host layer provides two
  * callbacks (backed by torch.distributed) that are used only at SETUP time: an allgather of small
  * byte blobs (to distribute the NCCL unique id) and a barrier.  The timed path never calls back
- * into Python: halo and inter-level messages are grouped ncclSend/ncclRecv on the compute stream,
- * norms are an 8-byte ncclAllReduce on a device scalar. */
+ * into Python: ghost exchanges are direct peer stores into the neighbour GPU's receive buffer plus a
+ * flag (CUDA IPC over NVLink; comm.cu), inter-level messages are grouped ncclSend/ncclRecv on the
+ * compute stream, norms are an 8-byte ncclAllReduce on a device scalar. */
 typedef void (*hpgmg_allgather_fn)(const void *send, void *recv, size_t bytes_per_rank, void *ctx);
 typedef void (*hpgmg_barrier_fn)(void *ctx);
 void hpgmg_b200_set_comm(int my_rank, int num_ranks, hpgmg_allgather_fn allgather, hpgmg_barrier_fn barrier, void *ctx);
 void hpgmg_b200_comm_finalize(void);
+/* 1 if ghost exchanges go through direct peer stores (CUDA IPC over NVLink), 0 if through ncclSend/ncclRecv */
+int  hpgmg_b200_p2p_enabled(void);
 
 #ifdef __cplusplus
 }

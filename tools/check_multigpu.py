@@ -17,7 +17,7 @@ boxes = H.boxes_in_i ** 3
 gold = json.load(open(os.path.join(ROOT, "tests", "golden", "goldens.json")))["solves"].get(f"{log2} {boxes} gsrb")
 if rank == 0:
     ok = gold is not None and [n[0] for n in norms] == gold["norms"] and err == gold["error"]
-    print(f"world={world} cfg={log2} {bpr}/rank -> {boxes} boxes, levels={H.num_levels} graphs={graphs}")
+    print(f"world={world} cfg={log2} {bpr}/rank -> {boxes} boxes, levels={H.num_levels} graphs={graphs} p2p={L.hpgmg_b200_p2p_enabled()}")
     print("  norms", [repr(n[0]) for n in norms], "error", repr(err), "order", round(order, 3))
     print("  golden", gold["norms"] if gold else None, gold["error"] if gold else None)
     print("  PARITY", "OK (bit-exact)" if ok else "MISMATCH")
