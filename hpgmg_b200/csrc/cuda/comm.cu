@@ -115,10 +115,11 @@ extern "C" void hpgmg_comm_allreduce_slot_max(level_type *level, int slot)
   g_launches++;
 }
 
-static double allreduce_host_value(level_type *level, double v, int op, const char *what)
+static double allreduce_host_value(level_type *level, double v, int op, const char *what, int world)
 {
-  if (level->num_ranks <= 1 || g_nranks <= 1) return v;
-  require_world(level, what);
+  if (g_nranks <= 1 || (!world && level->num_ranks <= 1)) return v;
+  if (world) { if (!g_comm) { fprintf(stderr, "hpgmg_b200: %s needs a communicator\n", what); exit(1); } }
+  else require_world(level, what);
   const int slot = HPGMG_SLOT_SCRATCH + 3;
   double *s = hpgmg_rt_scalar_slots() + slot;
   CUDA_CHECK(cudaMemcpyAsync(s, &v, sizeof(double), cudaMemcpyHostToDevice, g_stream));
@@ -128,8 +129,11 @@ static double allreduce_host_value(level_type *level, double v, int op, const ch
   hpgmg_rt_read_scalars(&r, slot, 1);
   return r;
 }
-extern "C" double hpgmg_comm_allreduce_max(level_type *level, double v) { return allreduce_host_value(level, v, ncclMax, "max-reduction"); }
-extern "C" double hpgmg_comm_allreduce_sum(level_type *level, double v) { return allreduce_host_value(level, v, ncclSum, "sum-reduction"); }
+/* over the ranks that share the level (MPI_COMM_ALLREDUCE of the reference) */
+extern "C" double hpgmg_comm_allreduce_max(level_type *level, double v) { return allreduce_host_value(level, v, ncclMax, "max-reduction", 0); }
+extern "C" double hpgmg_comm_allreduce_sum(level_type *level, double v) { return allreduce_host_value(level, v, ncclSum, "sum-reduction", 0); }
+/* over ALL ranks, whatever the level's rank count: the reference reduces lambda_max on MPI_COMM_WORLD (rebuild.c:195) */
+extern "C" double hpgmg_comm_allreduce_max_world(level_type *level, double v) { return allreduce_host_value(level, v, ncclMax, "max-reduction (world)", 1); }
 
 /* ---- point-to-point ------------------------------------------------------------------------------ */
 /* ghost exchange of one level: receive into recv_buffers, send from send_buffers (both sides use the

@@ -274,7 +274,7 @@ extern "C" void rebuild_operator_blackbox(level_type *level, double a, double b,
   double eig = 0.0;
   hpgmg_rt_read_scalars(&eig, HPGMG_SLOT_SCRATCH, 1);
   if (L.nboxes == 0) eig = -1e9;
-  eig = hpgmg_comm_allreduce_max(level, eig);          /* MPI_Allreduce(MAX) over all ranks (rebuild.c:195) */
+  eig = hpgmg_comm_allreduce_max_world(level, eig);    /* MPI_Allreduce(MAX) on MPI_COMM_WORLD (rebuild.c:195) */
   if (chatty) fprintf(stdout, "done\n");
   if (chatty && hpgmg_rt_smoother() == HPGMG_SMOOTHER_CHEBY) { fprintf(stdout, "  estimating  lambda_max... <%1.15e\n", eig); fflush(stdout); }
   level->dominant_eigenvalue_of_DinvA = eig;

@@ -81,6 +81,7 @@ int    hpgmg_comm_size(void);
 void   hpgmg_comm_barrier(void);
 double hpgmg_comm_allreduce_max(level_type *level, double v);
 double hpgmg_comm_allreduce_sum(level_type *level, double v);
+double hpgmg_comm_allreduce_max_world(level_type *level, double v);
 void   hpgmg_comm_allreduce_slot_max(level_type *level, int slot);
 void   hpgmg_comm_exchange(level_type *level, communicator_type *C, int tag);
 void   hpgmg_comm_exchange_wait(level_type *level, communicator_type *C);
