@@ -172,16 +172,12 @@ extern "C" void hpgmg_comm_transfer_wait(level_type *level_send, communicator_ty
  * of launch latency per message group dominates a multigrid cycle made of ~400 tiny exchanges).
  *
  * Every rank owns one "comm arena" of device memory, exported once with CUDA IPC and mapped by all
- * peers.  Receive buffers of the ghost exchange and two flags per neighbour live in it:
- *   - the SENDER's pack kernel copies its faces/edges/corners straight into the RECEIVER's buffer
- *     (NVLink stores, no staging copy, no NCCL) and then publishes the message by writing the
- *     exchange's sequence number into the receiver's DATA flag (system-scope release);
- *   - the receiver's unpack kernel spins on that flag (acquire), copies buffer -> ghost cells and
- *     acknowledges by writing the sequence number into the sender's ACK flag; the sender's next pack
- *     waits for that ACK before it overwrites the buffer (normally long since satisfied).
- * Sequence numbers live in device memory and are advanced by the kernels themselves, so the whole
- * thing is capturable in the solve's CUDA graph; the host never waits.  Order of messages and buffer
- * layout are the reference's (level.c:79-92, 724, 878).
+ * peers.  The slot arrays of the LL protocol (p2p.cuh) live in it: the SENDER's pack blocks store
+ * their faces/edges/corners straight into the RECEIVER's slots, the receiver's unpack blocks poll
+ * them -- inside the same kernel that does the GPU-local part of the ghost fill (ghost.cu).  Sequence
+ * numbers live in device memory and are advanced by the kernel itself, so everything is capturable in
+ * the solve's CUDA graph; the host never waits.  Message contents and order are the reference's
+ * (level.c:79-92, 724, 878).
  * ================================================================================================ */
 #include <map>
 #include <vector>
@@ -246,9 +242,9 @@ static void p2p_setup(void)
 }
 
 struct P2PWire {                                   /* what a rank tells the others about one communicator */
-  int nrecv, nsend;
-  int recv_from[P2P_MAX_NEIGHBOURS];  long long recv_buf_off[P2P_MAX_NEIGHBOURS], data_flag_off[P2P_MAX_NEIGHBOURS];
-  int send_to[P2P_MAX_NEIGHBOURS];    long long ack_flag_off[P2P_MAX_NEIGHBOURS];
+  int nrecv;
+  int recv_from[P2P_MAX_NEIGHBOURS], recv_size[P2P_MAX_NEIGHBOURS];
+  long long ll_off[P2P_MAX_NEIGHBOURS];            /* offset of the 2 x recv_size slot arrays in my arena */
 };
 
 extern "C" void hpgmg_comm_register_exchange(level_type *level, int shape)
@@ -257,47 +253,37 @@ extern "C" void hpgmg_comm_register_exchange(level_type *level, int shape)
   communicator_type *C = &level->exchange_ghosts[shape];
   P2PWire mine;
   memset(&mine, 0, sizeof(mine));
-  int fits = (C->num_recvs <= P2P_MAX_NEIGHBOURS && C->num_sends <= P2P_MAX_NEIGHBOURS);
-  unsigned long long *flags = NULL;
-  if (fits && (C->num_recvs + C->num_sends) > 0) flags = (unsigned long long *)hpgmg_rt_alloc_comm(sizeof(unsigned long long) * (size_t)(C->num_recvs + C->num_sends));
+  const int fits = (C->num_recvs <= P2P_MAX_NEIGHBOURS && C->num_sends <= P2P_MAX_NEIGHBOURS);
+  P2PPlan h;
+  memset(&h, 0, sizeof(h));
   if (fits) {
-    mine.nrecv = C->num_recvs;  mine.nsend = C->num_sends;
+    mine.nrecv = C->num_recvs;
     for (int n = 0; n < C->num_recvs; n++) {
+      uint4 *slots = (uint4 *)hpgmg_rt_alloc_comm(sizeof(uint4) * 2 * (size_t)C->recv_sizes[n]);
+      h.ll_local[n] = slots;
+      h.recv_size[n] = C->recv_sizes[n];
       mine.recv_from[n] = C->recv_ranks[n];
-      mine.recv_buf_off[n] = hpgmg_rt_is_comm_memory(C->recv_buffers[n]) ? (long long)((char *)C->recv_buffers[n] - g_arena) : -1;
-      mine.data_flag_off[n] = (long long)((char *)(flags + n) - g_arena);
+      mine.recv_size[n] = C->recv_sizes[n];
+      mine.ll_off[n] = (long long)((char *)slots - g_arena);
     }
-    for (int n = 0; n < C->num_sends; n++) {
-      mine.send_to[n] = C->send_ranks[n];
-      mine.ack_flag_off[n] = (long long)((char *)(flags + C->num_recvs + n) - g_arena);
-    }
-  } else mine.nrecv = mine.nsend = -1;
+  } else mine.nrecv = -1;
   std::vector<P2PWire> all((size_t)g_nranks);
   g_allgather(&mine, all.data(), sizeof(P2PWire), g_comm_ctx);
   for (int r = 0; r < g_nranks; r++) if (all[r].nrecv < 0) return;            /* somebody cannot: everybody keeps NCCL for this one */
   if (C->num_recvs + C->num_sends == 0) return;
 
-  P2PPlan h;
-  memset(&h, 0, sizeof(h));
-  std::vector<double *> remote_buf((size_t)C->num_sends, (double *)NULL);
   for (int n = 0; n < C->num_sends; n++) {
     const int R = C->send_ranks[n];
     int found = -1;
     for (int m = 0; m < all[R].nrecv; m++) if (all[R].recv_from[m] == g_rank) found = m;
-    if (found < 0 || all[R].recv_buf_off[found] < 0) { fprintf(stderr, "hpgmg_b200: rank %d has no receive buffer for rank %d\n", R, g_rank); exit(1); }
-    remote_buf[n] = (double *)(g_peer_arena[R] + all[R].recv_buf_off[found]);
-    h.remote_data_flag[n] = (unsigned long long *)(g_peer_arena[R] + all[R].data_flag_off[found]);
-    h.local_ack_flag[n] = flags + C->num_recvs + n;
+    if (found < 0 || all[R].recv_size[found] != C->send_sizes[n]) {
+      fprintf(stderr, "hpgmg_b200: rank %d expects %d doubles from rank %d, which sends %d\n", R, found < 0 ? -1 : all[R].recv_size[found], g_rank, C->send_sizes[n]);
+      exit(1);
+    }
+    h.ll_remote[n] = (uint4 *)(g_peer_arena[R] + all[R].ll_off[found]);
+    h.send_size[n] = C->send_sizes[n];
   }
-  for (int n = 0; n < C->num_recvs; n++) {
-    const int S = C->recv_ranks[n];
-    int found = -1;
-    for (int m = 0; m < all[S].nsend; m++) if (all[S].send_to[m] == g_rank) found = m;
-    if (found < 0) { fprintf(stderr, "hpgmg_b200: rank %d does not send to rank %d\n", S, g_rank); exit(1); }
-    h.local_data_flag[n] = flags + n;
-    h.remote_ack_flag[n] = (unsigned long long *)(g_peer_arena[S] + all[S].ack_flag_off[found]);
-  }
-  /* device copies of the pack / unpack lists: pack writes go to the REMOTE buffers; subtype = neighbour */
+  /* device copies of the pack / unpack lists with subtype = neighbour index */
   P2PHost H;
   memset(&H, 0, sizeof(H));
   std::vector<blockCopy_type> pack(C->blocks[0], C->blocks[0] + C->num_blocks[0]), unpack(C->blocks[2], C->blocks[2] + C->num_blocks[2]);
@@ -305,16 +291,13 @@ extern "C" void hpgmg_comm_register_exchange(level_type *level, int shape)
     int n = -1;
     for (int m = 0; m < C->num_sends; m++) if (pack[e].write.ptr == C->send_buffers[m]) n = m;
     if (n < 0) { fprintf(stderr, "hpgmg_b200: pack entry without a send buffer\n"); exit(1); }
-    pack[e].write.ptr = remote_buf[n];
     pack[e].subtype = n;
-    h.send_blocks[n]++;
   }
   for (size_t e = 0; e < unpack.size(); e++) {
     int n = -1;
     for (int m = 0; m < C->num_recvs; m++) if (unpack[e].read.ptr == C->recv_buffers[m]) n = m;
     if (n < 0) { fprintf(stderr, "hpgmg_b200: unpack entry without a receive buffer\n"); exit(1); }
     unpack[e].subtype = n;
-    h.recv_blocks[n]++;
   }
   H.npack = (int)pack.size();  H.nunpack = (int)unpack.size();
   if (H.npack) { CUDA_CHECK(cudaMalloc(&H.pack, pack.size() * sizeof(blockCopy_type))); CUDA_CHECK(cudaMemcpy(H.pack, pack.data(), pack.size() * sizeof(blockCopy_type), cudaMemcpyHostToDevice)); }

@@ -14,6 +14,7 @@
  * order the reference's face / edge (16-point) / corner (64-point) code uses -- so results are
  * bit-identical.
  */
+#include <string.h>
 #include "common.cuh"
 #include "p2p.cuh"
 
@@ -109,23 +110,20 @@ __global__ void bc_v1_kernel(const DLevel L, const int id, const blockCopy_type 
   }
 }
 
-/* ---- fused ghost fill: exchange_boundary + apply_BCs ---------------------------------------------- */
-/* One fill is at most TWO kernels:
- *
- *  send_fill_kernel   blocks [0, npack)  : one pack-list entry each -- copy box cells straight into the
- *                                          neighbour GPU's receive buffer over NVLink, then publish the
- *                                          message (p2p protocol, comm.cu);          [multi-GPU only]
- *                     remaining blocks   : 256 work items each -- an item is either one ghost cell copied
- *                                          from the neighbouring box on this GPU, or one BC column, which
- *                                          reads its interior values straight from the box that owns them
- *                                          (FillBC::src), so copies and BCs are independent.
- *  recv_fill_kernel   blocks [0, nunpack): wait for the neighbour's message, copy buffer -> ghost cells,
- *                                          acknowledge;                              [multi-GPU only]
- *                     remaining blocks   : the BC columns that need those ghost cells; they wait (in-kernel
- *                                          counter) until every unpack block of this launch has finished.
- *                                          Blocks are dispatched in index order, so the unpack blocks are
- *                                          always resident or finished before a waiting block exists.
- * version: 4 quartic, 2 quadratic (also zeroes the deeper ghost layer, like the reference). */
+/* ---- fused ghost fill: exchange_boundary + apply_BCs in ONE kernel ------------------------------- */
+/* Thread blocks of a fill, in dispatch order:
+ *   [0, npack)                 one pack-list entry each: box cells -> LL slots in the neighbour GPU's
+ *                              memory (NVLink stores, p2p.cuh); never waits;              [multi-GPU]
+ *   [npack, +fill blocks)      256 work items each: an item is either one ghost cell copied from the
+ *                              neighbouring box on this GPU, or one BC column, which reads its interior
+ *                              values straight from the box that owns them (FillBC::src), so copies
+ *                              and BCs are independent of each other;
+ *   [.., +nunpack)             one unpack-list entry each: poll my LL slots until the neighbour's data of
+ *                              this exchange has arrived, write the ghost cells;          [multi-GPU]
+ *   [.., +late blocks)         the BC columns that read those ghost cells: they wait on an in-kernel
+ *                              counter until every unpack block has finished.              [multi-GPU]
+ * Blocks are dispatched in index order, so a waiting block never keeps the block it waits for off the
+ * machine.  version: 4 quartic, 2 quadratic (also zeroes the deeper ghost layer, like the reference). */
 __device__ __forceinline__ void fill_items(const DLevel &L, const int id, const int t, const FillCopy *__restrict__ copies, const int ncopies,
                                            const FillBC *__restrict__ bc, const int nbc, const int version)
 {
@@ -141,94 +139,70 @@ __device__ __forceinline__ void fill_items(const DLevel &L, const int id, const 
   }
 }
 
-__global__ void __launch_bounds__(256) send_fill_kernel(const DLevel L, const int id, const blockCopy_type *__restrict__ pack, const int npack, P2PPlan *plan,
-                                                        const FillCopy *__restrict__ copies, const int ncopies, const FillBC *__restrict__ bc, const int nbc, const int version)
-{
-  if ((int)blockIdx.x >= npack) {
-    fill_items(L, id, ((int)blockIdx.x - npack) * blockDim.x + threadIdx.x, copies, ncopies, bc, nbc, version);
-    return;
-  }
-  const blockCopy_type B = pack[blockIdx.x];
-  const int n = B.subtype;                                            /* neighbour index (set in comm.cu) */
-  __shared__ unsigned long long epoch_s;
-  if (threadIdx.x == 0) {
-    const unsigned long long epoch = *(volatile unsigned long long *)&plan->epoch_send;
-    while (ld_acquire_sys(plan->local_ack_flag[n]) < epoch) { }      /* the receiver has drained the previous message */
-    epoch_s = epoch;
-  }
-  __syncthreads();
-  const double *__restrict__ rd = L.vec(B.read.box, id) + B.read.i + B.read.j * L.jStride + B.read.k * L.kStride;
-  double *wr = B.write.ptr + B.write.i + B.write.j * B.write.jStride + B.write.k * B.write.kStride;
-  const int di = B.dim.i, dj = B.dim.j, cells = di * dj * B.dim.k;
-  for (int c = threadIdx.x; c < cells; c += blockDim.x) {
-    const int i = c % di, j = (c / di) % dj, k = c / (di * dj);
-    wr[i + j * B.write.jStride + k * B.write.kStride] = rd[i + j * L.jStride + k * L.kStride];
-  }
-  __syncthreads();                                                    /* every thread's stores are ordered before thread 0's fence */
-  if (threadIdx.x == 0) {
-    const unsigned long long epoch = epoch_s;
-    __threadfence_system();
-    if (atomicAdd(&plan->send_count[n], 1u) == (unsigned)plan->send_blocks[n] - 1u) {   /* last entry for this neighbour */
-      plan->send_count[n] = 0;
-      __threadfence_system();
-      st_release_sys(plan->remote_data_flag[n], epoch + 1);
-    }
-    if (atomicAdd(&plan->done_send, 1u) == (unsigned)npack - 1u) {                        /* last pack block of the launch */
-      plan->done_send = 0;
-      __threadfence();
-      *(volatile unsigned long long *)&plan->epoch_send = epoch + 1;
-    }
-  }
-}
+struct FillArgs {
+  DLevel L;
+  int id, version;
+  const blockCopy_type *pack, *unpack;
+  int npack, nfill_blocks, nunpack, nlate_blocks;
+  P2PPlan *plan;
+  const FillCopy *copies;  int ncopies;
+  const FillBC *bc;        int nbc;
+  const FillBC *late;      int nlate;
+};
 
-__global__ void __launch_bounds__(256) recv_fill_kernel(const DLevel L, const int id, const blockCopy_type *__restrict__ unpack, const int nunpack, P2PPlan *plan,
-                                                        const FillBC *__restrict__ late, const int nlate, const int nlate_blocks, const int version)
+__global__ void __launch_bounds__(256) fill_ghosts_kernel(const FillArgs A)
 {
-  if ((int)blockIdx.x >= nunpack) {                                   /* BC columns that read unpacked ghost cells */
-    if (threadIdx.x == 0) {
-      while (*(volatile unsigned int *)&plan->done_recv < (unsigned)nunpack) { }
-      __threadfence();
-    }
-    __syncthreads();
-    fill_items(L, id, ((int)blockIdx.x - nunpack) * blockDim.x + threadIdx.x, (const FillCopy *)nullptr, 0, late, nlate, version);
-    __syncthreads();
-    if (threadIdx.x == 0 && atomicAdd(&plan->late_passed, 1u) == (unsigned)nlate_blocks - 1u) {
-      plan->late_passed = 0;
-      plan->done_recv = 0;                                            /* re-arm for the next launch */
-    }
+  const DLevel &L = A.L;
+  int b = blockIdx.x;
+  if (b >= A.npack && b < A.npack + A.nfill_blocks && A.plan == nullptr) {            /* single-GPU fast path */
+    fill_items(L, A.id, (b - A.npack) * blockDim.x + threadIdx.x, A.copies, A.ncopies, A.bc, A.nbc, A.version);
     return;
   }
-  const blockCopy_type B = unpack[blockIdx.x];
-  const int n = B.subtype;
-  __shared__ unsigned long long epoch_s;
-  if (threadIdx.x == 0) {
-    const unsigned long long epoch = *(volatile unsigned long long *)&plan->epoch_recv;
-    while (ld_acquire_sys(plan->local_data_flag[n]) < epoch + 1) { }  /* the sender's stores have landed */
-    epoch_s = epoch;
-  }
-  __syncthreads();
-  const double *rd = B.read.ptr + B.read.i + B.read.j * B.read.jStride + B.read.k * B.read.kStride;
-  double *__restrict__ wr = L.vec(B.write.box, id) + B.write.i + B.write.j * L.jStride + B.write.k * L.kStride;
-  const int di = B.dim.i, dj = B.dim.j, cells = di * dj * B.dim.k;
-  for (int c = threadIdx.x; c < cells; c += blockDim.x) {
-    const int i = c % di, j = (c / di) % dj, k = c / (di * dj);
-    wr[i + j * L.jStride + k * L.kStride] = __ldcv(rd + i + j * B.read.jStride + k * B.read.kStride);
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned long long epoch = epoch_s;
-    __threadfence();
-    if (atomicAdd(&plan->recv_count[n], 1u) == (unsigned)plan->recv_blocks[n] - 1u) {
-      plan->recv_count[n] = 0;
-      __threadfence_system();
-      st_release_sys(plan->remote_ack_flag[n], epoch + 1);            /* the sender may reuse the buffer */
+  P2PPlan *plan = A.plan;
+  const unsigned long long epoch = *(volatile unsigned long long *)&plan->epoch;      /* bumped only after every block is done */
+  const unsigned flag = (unsigned)(epoch + 1);
+  const int parity = (int)(epoch & 1);
+  if (b < A.npack) {                                                                   /* ---- pack ---- */
+    const blockCopy_type B = A.pack[b];
+    const int n = B.subtype;
+    uint4 *slots = plan->ll_remote[n] + (size_t)parity * plan->send_size[n];
+    const double *__restrict__ rd = L.vec(B.read.box, A.id) + B.read.i + B.read.j * L.jStride + B.read.k * L.kStride;
+    const int di = B.dim.i, dj = B.dim.j, cells = di * dj * B.dim.k;
+    const int w0 = B.write.i + B.write.j * B.write.jStride + B.write.k * B.write.kStride;
+    for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+      const int i = c % di, j = (c / di) % dj, k = c / (di * dj);
+      ll_store(slots + w0 + i + j * B.write.jStride + k * B.write.kStride, rd[i + j * L.jStride + k * L.kStride], flag);
     }
-    const unsigned int done = atomicAdd(&plan->done_recv, 1u);
-    if (done == (unsigned)nunpack - 1u) {                              /* last unpack block of the launch */
+  } else if ((b -= A.npack) < A.nfill_blocks) {                                        /* ---- GPU-local copies + BCs ---- */
+    fill_items(L, A.id, b * blockDim.x + threadIdx.x, A.copies, A.ncopies, A.bc, A.nbc, A.version);
+  } else if ((b -= A.nfill_blocks) < A.nunpack) {                                      /* ---- unpack ---- */
+    const blockCopy_type B = A.unpack[b];
+    const int n = B.subtype;
+    const uint4 *slots = plan->ll_local[n] + (size_t)parity * plan->recv_size[n];
+    double *__restrict__ wr = L.vec(B.write.box, A.id) + B.write.i + B.write.j * L.jStride + B.write.k * L.kStride;
+    const int di = B.dim.i, dj = B.dim.j, cells = di * dj * B.dim.k;
+    const int r0 = B.read.i + B.read.j * B.read.jStride + B.read.k * B.read.kStride;
+    for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+      const int i = c % di, j = (c / di) % dj, k = c / (di * dj);
+      wr[i + j * L.jStride + k * L.kStride] = ll_load(slots + r0 + i + j * B.read.jStride + k * B.read.kStride, flag);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); atomicAdd(&plan->unpack_done, 1u); }
+  } else {                                                                             /* ---- BC columns behind unpacked cells ---- */
+    b -= A.nunpack;
+    if (threadIdx.x == 0) {
+      while (*(volatile unsigned int *)&plan->unpack_done < (unsigned)A.nunpack) { }
       __threadfence();
-      *(volatile unsigned long long *)&plan->epoch_recv = epoch + 1;
-      if (nlate_blocks == 0) plan->done_recv = 0;                      /* nobody else will re-arm it */
     }
+    __syncthreads();
+    fill_items(L, A.id, b * blockDim.x + threadIdx.x, (const FillCopy *)nullptr, 0, A.late, A.nlate, A.version);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && atomicAdd(&plan->done, 1u) == gridDim.x - 1u) {              /* last block: re-arm, advance */
+    plan->done = 0;
+    plan->unpack_done = 0;
+    __threadfence();
+    *(volatile unsigned long long *)&plan->epoch = epoch + 1;
   }
 }
 
@@ -254,15 +228,19 @@ void hpgmg_fill_ghosts(level_type *level, int id, int shape, int bc_version)
     if (bc_version == 4) apply_BCs_v4(level, id, shape); else if (bc_version == 2) apply_BCs_v2(level, id, shape);
     return;
   }
-  const int nbc = dirichlet ? T.nbc : 0, nlate = dirichlet ? T.nlate : 0;
-  const int fill_blocks = (T.ncopies + nbc + 255) / 256;
-  if (npack + fill_blocks > 0)
-    LAUNCH(send_fill_kernel, npack + fill_blocks, 256, 0, D->L, id, pack, npack, plan, T.copies, T.ncopies, T.bc, nbc, version);
+  FillArgs A;
+  memset(&A, 0, sizeof(A));
+  A.L = D->L;  A.id = id;  A.version = version;
+  A.copies = T.copies;  A.ncopies = T.ncopies;
+  A.bc = T.bc;          A.nbc = dirichlet ? T.nbc : 0;
+  A.nfill_blocks = (A.ncopies + A.nbc + 255) / 256;
   if (remote) {
-    const int late_blocks = (nlate + 255) / 256;
-    if (nunpack + late_blocks > 0)
-      LAUNCH(recv_fill_kernel, nunpack + late_blocks, 256, 0, D->L, id, unpack, nunpack, plan, T.late, nlate, late_blocks, version);
+    A.pack = pack;  A.npack = npack;  A.unpack = unpack;  A.nunpack = nunpack;  A.plan = plan;
+    A.late = T.late;  A.nlate = dirichlet ? T.nlate : 0;
+    A.nlate_blocks = (A.nlate + 255) / 256;
   }
+  const int blocks = A.npack + A.nfill_blocks + A.nunpack + A.nlate_blocks;
+  if (blocks > 0) LAUNCH(fill_ghosts_kernel, blocks, 256, 0, A);
 }
 
 extern "C" void apply_BCs_v1(level_type *level, int x_id, int shape)

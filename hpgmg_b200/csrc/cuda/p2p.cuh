@@ -1,6 +1,15 @@
 /*
  * p2p.cuh -- device-side state and primitives of the direct peer-to-peer ghost exchange (see comm.cu for
- * the protocol and the setup, ghost.cu for the kernels).
+ * the setup, ghost.cu for the kernel).
+ *
+ * Protocol ("LL", the low-latency scheme NCCL uses for small messages): a message element is one
+ * 16-byte slot {lo32(data), flag, hi32(data), flag} written with a single 128-bit volatile store into
+ * the RECEIVER's memory over NVLink.  The flag is the exchange's sequence number, so the receiver
+ * simply polls the slot until both flags match -- data and "ready" travel in the same 8-byte-atomic
+ * units: no fences, no separate flag, no acknowledgement.  Each neighbour pair has TWO slot arrays
+ * used alternately (sequence parity).  Overwriting array p at exchange k+2 is safe because ghost
+ * exchange is symmetric: I only get there after unpacking the neighbour's message k+1, which it sent
+ * after it had unpacked my message k.
  */
 #ifndef HPGMG_B200_P2P_CUH
 #define HPGMG_B200_P2P_CUH
@@ -9,26 +18,25 @@
 #define P2P_MAX_NEIGHBOURS 32
 
 struct P2PPlan {                                   /* device-resident state of one communicator */
-  unsigned long long epoch_send, epoch_recv;       /* messages sent / received so far */
-  unsigned int done_send, done_recv, late_passed;  /* thread blocks finished in the current kernel */
-  unsigned int send_count[P2P_MAX_NEIGHBOURS], recv_count[P2P_MAX_NEIGHBOURS];
-  int send_blocks[P2P_MAX_NEIGHBOURS], recv_blocks[P2P_MAX_NEIGHBOURS];   /* list entries per neighbour */
-  unsigned long long *remote_data_flag[P2P_MAX_NEIGHBOURS];   /* in the receiver's arena: I write */
-  unsigned long long *local_ack_flag[P2P_MAX_NEIGHBOURS];     /* in my arena: receiver writes, my pack waits */
-  unsigned long long *local_data_flag[P2P_MAX_NEIGHBOURS];    /* in my arena: sender writes, my unpack waits */
-  unsigned long long *remote_ack_flag[P2P_MAX_NEIGHBOURS];    /* in the sender's arena: I write */
+  unsigned long long epoch;                        /* exchanges completed so far */
+  unsigned int done, unpack_done;                  /* thread blocks finished in the current launch */
+  int send_size[P2P_MAX_NEIGHBOURS], recv_size[P2P_MAX_NEIGHBOURS];   /* doubles per message */
+  uint4 *ll_remote[P2P_MAX_NEIGHBOURS];            /* 2 x send_size slots in the receiver's arena: I write */
+  uint4 *ll_local[P2P_MAX_NEIGHBOURS];             /* 2 x recv_size slots in my arena: the sender writes, I poll */
 };
 
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+__device__ __forceinline__ void ll_store(uint4 *slot, const double v, const unsigned flag)
 {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
+  const unsigned lo = (unsigned)__double2loint(v), hi = (unsigned)__double2hiint(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(slot), "r"(lo), "r"(flag), "r"(hi), "r"(flag) : "memory");
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+__device__ __forceinline__ double ll_load(const uint4 *slot, const unsigned flag)
 {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+  unsigned lo, f0, hi, f1;
+  do {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f0), "=r"(hi), "=r"(f1) : "l"(slot) : "memory");
+  } while (f0 != flag || f1 != flag);
+  return __hiloint2double((int)hi, (int)lo);
 }
 
 int hpgmg_comm_p2p_lookup(level_type *level, int shape, const blockCopy_type **pack, int *npack, const blockCopy_type **unpack, int *nunpack, P2PPlan **plan);

@@ -43,13 +43,16 @@ def time_op(name, fn, reps=20):
         print(f"   {name}: {1e3 * L.hpgmg_b200_bench_elapsed_ms(0, 1) / reps:.1f} us", flush=True)
 
 
-for lvl in (0, 1, 2, 3):
+for lvl in range(0, H.num_levels - 2):
     lv = H.level(lvl)
     if rank == 0:
         print(f" level {lvl} dim {lv.contents.dim.i} boxes/rank {lv.contents.num_my_boxes}")
     time_op("exchange_boundary(NO_CORNERS)", lambda: L.exchange_boundary(lv, api.VECTOR_E, 2))
     time_op("smooth (6 sweeps)", lambda: L.smooth(lv, api.VECTOR_E, api.VECTOR_R, 0.0, 1.0))
     time_op("residual", lambda: L.residual(lv, api.VECTOR_TEMP, api.VECTOR_E, api.VECTOR_R, 0.0, 1.0))
+    lc = H.level(lvl + 1)
+    time_op("restriction -> coarser", lambda: L.restriction(lc, api.VECTOR_R, lv, api.VECTOR_TEMP, 0))
+    time_op("interpolation_v2 <- coarser", lambda: L.interpolation_vcycle(lv, api.VECTOR_E, 1.0, lc, api.VECTOR_E))
 H.close()
 if world > 1:
     import torch.distributed as dist
