@@ -27,6 +27,7 @@ struct BlasArgs {
 template <int OP>
 __global__ void __launch_bounds__(256) blas1_kernel(const BlasArgs A)
 {
+  PDL_WAIT();
   const DLevel &L = A.L;
   const int g = (OP == B_ZERO || OP == B_INIT) ? L.ghosts : 0;      /* these two cover the ghost zones */
   const int n = L.dim + 2 * g;
@@ -93,6 +94,7 @@ extern "C" void random_vector(level_type *level, int id_a)
 /* ---- max norm ---------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(256) norm_kernel(const DLevel L, const int id, double *__restrict__ slot)
 {
+  PDL_WAIT();
   const int n = L.dim, cells = n * n * n, box = blockIdx.y;
   const double *__restrict__ v = L.vec(box, id);
   double m = 0.0;
@@ -144,6 +146,7 @@ extern "C" double hpgmg_level_norm(level_type *level, int id_a)
 __global__ void tile_sum_kernel(const DLevel L, const int id_a, const int id_b, const blockCopy_type *__restrict__ tiles, const int ntiles,
                                 double *__restrict__ partials, const int mode)
 {
+  PDL_WAIT();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= ntiles) return;
   const blockCopy_type B = tiles[t];
@@ -161,6 +164,7 @@ __global__ void tile_sum_kernel(const DLevel L, const int id_a, const int id_b, 
 }
 __global__ void ordered_total_kernel(const double *__restrict__ partials, const int n, double *__restrict__ slot)
 {
+  PDL_WAIT();
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     double s = 0.0;
     for (int t = 0; t < n; t++) s += partials[t];

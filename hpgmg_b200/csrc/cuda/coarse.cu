@@ -234,6 +234,7 @@ __device__ static void c_vcycle(const CoarseArgs &A, const int c, double *prod, 
  * read-only operator data (Dinv, betas) is written back at the end. */
 __global__ void __launch_bounds__(COARSE_THREADS, 1) coarse_cycle_kernel(const __grid_constant__ CoarseArgs Ain)
 {
+  PDL_WAIT();
   extern __shared__ __align__(16) double dyn[];
   CoarseArgs &A = *reinterpret_cast<CoarseArgs *>(dyn);
   constexpr int ARGS_DOUBLES = (int)((sizeof(CoarseArgs) + 15) / 16) * 2;

@@ -13,6 +13,7 @@
 #include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "hpgmg_b200.h"
 #include "../runtime.h"
@@ -24,15 +25,30 @@ extern int g_capturing;                         /* inside a stream capture?     
 void hpgmg_cuda_check(cudaError_t e, const char *what, const char *file, int line);
 #define CUDA_CHECK(x) hpgmg_cuda_check((x), #x, __FILE__, __LINE__)
 
-/* launch on the compute stream and count it */
+/* Launch on the compute stream and count it.  Kernels are launched with programmatic stream
+ * serialization (programmatic dependent launch): the next kernel's blocks may be scheduled while the
+ * previous kernel drains, and every kernel starts with PDL_WAIT() (griddepcontrol.wait), which
+ * blocks until the previous kernel's memory operations are complete and visible.  On the hundreds of
+ * microsecond-sized kernels of the coarse levels this hides most of the launch gap. */
+#define PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+extern int g_use_pdl;
 void hpgmg_refuse_launch(const char *kernel);
-#define LAUNCH(kernel, grid, block, smem, ...)                                  \
-  do {                                                                          \
-    if (hpgmg_rt_layout_only()) hpgmg_refuse_launch(#kernel);                   \
-    kernel<<<(grid), (block), (smem), g_stream>>>(__VA_ARGS__);                 \
-    g_launches++;                                                               \
-    CUDA_CHECK(cudaGetLastError());                                             \
-  } while (0)
+template <typename... KArgs, typename... Args>
+static inline void hpgmg_launch(const char *name, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args)
+{
+  if (hpgmg_rt_layout_only()) hpgmg_refuse_launch(name);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;  cfg.blockDim = block;  cfg.dynamicSmemBytes = smem;  cfg.stream = g_stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  g_launches++;
+}
+#define LAUNCH(kernel, grid, block, smem, ...) hpgmg_launch(#kernel, kernel, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__)
 
 /* One level's HBM layout, passed by value to kernels: a single slab [box][vector][k][j][i], every
  * box the same padded cube (reference level.c:935-938).  vec(b,id) points at cell (0,0,0). */

@@ -21,6 +21,7 @@
 /* ---- copy lists ------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(128) copy_blocks_kernel(const DLevel L, const int id, const blockCopy_type *__restrict__ blocks)
 {
+  PDL_WAIT();
   const blockCopy_type B = blocks[blockIdx.x];
   const double *__restrict__ rd;
   double *__restrict__ wr;
@@ -76,11 +77,13 @@ extern "C" void exchange_boundary(level_type *level, int id, int shape)
 
 __global__ void __launch_bounds__(128) bc_v4_kernel(const DLevel L, const int id, const blockCopy_type *__restrict__ blocks)
 {
+  PDL_WAIT();
   const blockCopy_type B = blocks[blockIdx.x];
   bc_v4_block(L, id, B, threadIdx.x, blockDim.x);
 }
 __global__ void __launch_bounds__(128) bc_v2_kernel(const DLevel L, const int id, const blockCopy_type *__restrict__ blocks)
 {
+  PDL_WAIT();
   const blockCopy_type B = blocks[blockIdx.x];
   bc_v2_block(L, id, B, threadIdx.x, blockDim.x);
 }
@@ -92,6 +95,7 @@ __global__ void __launch_bounds__(128) bc_v2_kernel(const DLevel L, const int id
  * exists for box_dim<2, which the radius-2 fv4 stencil never produces; kept for API completeness. */
 __global__ void bc_v1_kernel(const DLevel L, const int id, const blockCopy_type *__restrict__ blocks, const int nblocks)
 {
+  PDL_WAIT();
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
   for (int e = 0; e < nblocks; e++) {
     const blockCopy_type B = blocks[e];
@@ -152,6 +156,7 @@ struct FillArgs {
 
 __global__ void __launch_bounds__(256) fill_ghosts_kernel(const FillArgs A)
 {
+  PDL_WAIT();
   const DLevel &L = A.L;
   int b = blockIdx.x;
   if (b >= A.npack && b < A.npack + A.nfill_blocks && A.plan == nullptr) {            /* single-GPU fast path */
@@ -280,6 +285,7 @@ extern "C" void apply_BCs(level_type *level, int x_id, int shape) { apply_BCs_v4
  * result.  Setup only (untimed in the reference). */
 __global__ void extrapolate_betas_kernel(const DLevel L, const blockCopy_type *__restrict__ blocks, const int n)
 {
+  PDL_WAIT();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   const blockCopy_type B = blocks[e];

@@ -17,6 +17,8 @@
 cudaStream_t g_stream = 0;
 unsigned long long g_launches = 0;
 int g_capturing = 0;
+int g_use_pdl = 1;
+extern "C" void hpgmg_b200_use_pdl(int on) { g_use_pdl = on ? 1 : 0; }
 
 static int g_initialised = 0;
 static int g_device = -1;
@@ -85,6 +87,7 @@ extern "C" int hpgmg_b200_init(int device_ordinal)
     return 3;
   }
   g_device = device_ordinal;
+  { const char *e = getenv("HPGMG_B200_NO_PDL"); if (e && atoi(e)) g_use_pdl = 0; }
   CUDA_CHECK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
   CUDA_CHECK(cudaMalloc(&g_scalars, HPGMG_NUM_SCALARS * sizeof(double)));
   CUDA_CHECK(cudaMemset(g_scalars, 0, HPGMG_NUM_SCALARS * sizeof(double)));

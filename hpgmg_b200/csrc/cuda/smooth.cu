@@ -28,6 +28,7 @@ struct StencilArgs {
 template <int OP>
 __global__ void __launch_bounds__(256) stencil_generic_kernel(const StencilArgs A)
 {
+  PDL_WAIT();
   const DLevel &L = A.L;
   const int n = L.dim;
   const int ktiles = (n + blockDim.z - 1) / blockDim.z;
@@ -218,6 +219,7 @@ extern "C" void smooth(level_type *level, int x_id, int rhs_id, double a, double
 /* D^-1 and the Gershgorin bound on lambda_max(D^-1 A) from the operator alone (rebuild.c:47-208) */
 __global__ void rebuild_finish_kernel(const DLevel L, const int *low, int Aii_id, int sum_id, double a, double b, double h2inv, double *eig_slot)
 {
+  PDL_WAIT();
   const int n = L.dim;
   const int cells = n * n * n;
   double local = 0.0;                                  /* all Di are > 0 for this operator */

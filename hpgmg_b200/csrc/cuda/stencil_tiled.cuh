@@ -118,6 +118,7 @@ struct TileLoader {
 template <int OP, int TI, int TJ, bool ASYNC>
 __global__ void __launch_bounds__((TI / 2) * TJ, 2) stencil_tiled_kernel(const StencilArgs A, const int kchunk)
 {
+  PDL_WAIT();
   typedef TileCfg<TI, TJ> C;
   extern __shared__ __align__(16) double smem[];
   double *xs = smem;                              /* [XP][XR][W] */

@@ -18,6 +18,7 @@ void hpgmg_fill_ghosts(level_type *level, int id, int shape, int bc_version);
 __global__ void __launch_bounds__(128) restriction_kernel(const DLevel Lc, const int id_c, const DLevel Lf, const int id_f,
                                                           const blockCopy_type *__restrict__ blocks, const int type)
 {
+  PDL_WAIT();
   const blockCopy_type B = blocks[blockIdx.x];
   const double *__restrict__ rd;
   double *__restrict__ wr;
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(128) interpolation_kernel(const DLevel Lf, con
                                                             const DLevel Lc, const int id_c,
                                                             const blockCopy_type *__restrict__ blocks, const int force_zero_prescale)
 {
+  PDL_WAIT();
   constexpr int R = W / 2;
   const blockCopy_type B = blocks[blockIdx.x];
   const double *__restrict__ rd;
@@ -150,6 +152,7 @@ __global__ void __launch_bounds__(128) interpolation_kernel(const DLevel Lf, con
  * (IncrementBlock, blockCopy.c:108-156) */
 __global__ void __launch_bounds__(128) increment_blocks_kernel(const DLevel L, const int id, const double prescale, const blockCopy_type *__restrict__ blocks)
 {
+  PDL_WAIT();
   const blockCopy_type B = blocks[blockIdx.x];
   const double *__restrict__ rd;
   double *__restrict__ wr;
