@@ -48,6 +48,22 @@ static inline void hpgmg_launch(const char *name, void (*kernel)(KArgs...), dim3
   CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
   g_launches++;
 }
+/* cooperative launch: every block of the grid is resident at once (needed by kernels with a grid-wide barrier) */
+template <typename... KArgs, typename... Args>
+static inline void hpgmg_launch_cooperative(const char *name, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args)
+{
+  if (hpgmg_rt_layout_only()) hpgmg_refuse_launch(name);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;  cfg.blockDim = block;  cfg.dynamicSmemBytes = smem;  cfg.stream = g_stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  g_launches++;
+}
 #define LAUNCH(kernel, grid, block, smem, ...) hpgmg_launch(#kernel, kernel, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__)
 
 /* One level's HBM layout, passed by value to kernels: a single slab [box][vector][k][j][i], every

@@ -128,20 +128,7 @@ __global__ void bc_v1_kernel(const DLevel L, const int id, const blockCopy_type 
  *                              counter until every unpack block has finished.              [multi-GPU]
  * Blocks are dispatched in index order, so a waiting block never keeps the block it waits for off the
  * machine.  version: 4 quartic, 2 quadratic (also zeroes the deeper ghost layer, like the reference). */
-__device__ __forceinline__ void fill_items(const DLevel &L, const int id, const int t, const FillCopy *__restrict__ copies, const int ncopies,
-                                           const FillBC *__restrict__ bc, const int nbc, const int version)
-{
-  double *v = L.base + (size_t)id * (size_t)L.volume;
-  if (t < ncopies) {
-    const FillCopy c = copies[t];
-    v[c.dst] = v[c.src];
-  } else if (t < ncopies + nbc) {
-    const FillBC it = bc[t - ncopies];
-    const BCNormal N = bc_normal(it.subtype, L.jStride, L.kStride);
-    if (version == 4) bc_v4_column(v + it.src, v + it.dst, N);
-    else              bc_v2_col_zero_rest(v + it.src, v + it.dst, N.m, N.d[0], N.d[1], N.d[2]);
-  }
-}
+#include "fill.cuh"
 
 struct FillArgs {
   DLevel L;

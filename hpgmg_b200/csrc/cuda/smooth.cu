@@ -79,9 +79,26 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(const StencilArgs 
 
 #include "stencil_tiled.cuh"
 
-static int g_force_generic = -1, g_kchunk_override = -1;
-
 static int g_tiled_async = 1;
+static int g_force_generic = -1, g_kchunk_override = -1, g_tile32 = 0, g_min_chunk = 16, g_persistent_smooth = 0;
+
+static void stencil_env(void)
+{
+  if (g_force_generic < 0) {
+    const char *e = getenv("HPGMG_B200_GENERIC_STENCIL");
+    g_force_generic = (e && atoi(e)) ? 1 : 0;
+    const char *t32 = getenv("HPGMG_B200_TILE32");
+    if (t32) g_tile32 = atoi(t32);
+    const char *mc = getenv("HPGMG_B200_MIN_CHUNK");
+    if (mc) g_min_chunk = atoi(mc);
+    const char *ps = getenv("HPGMG_B200_PERSISTENT_SMOOTH");
+    if (ps) g_persistent_smooth = atoi(ps);
+    const char *as = getenv("HPGMG_B200_TILED_ASYNC");
+    if (as) g_tiled_async = atoi(as);
+    const char *kc = getenv("HPGMG_B200_KCHUNK");
+    if (kc) g_kchunk_override = atoi(kc);
+  }
+}
 
 template <int OP, int TI, int TJ>
 static void launch_tiled(const StencilArgs &A)
@@ -98,7 +115,7 @@ static void launch_tiled(const StencilArgs &A)
   /* split k so that the grid fills the 148 SMs x 2 resident blocks, but keep chunks >= 16 planes
    * (each chunk re-reads a 4-plane prologue) */
   int chunks = 1;
-  while (tiles * A.L.nboxes * chunks < 296 && n / (chunks * 2) >= 16) chunks *= 2;
+  while (tiles * A.L.nboxes * chunks < 296 && n / (chunks * 2) >= g_min_chunk) chunks *= 2;
   if (g_kchunk_override > 0) chunks = (n + g_kchunk_override - 1) / g_kchunk_override;
   const int kchunk = (n + chunks - 1) / chunks;
   dim3 grid(tiles, chunks, A.L.nboxes), block(TI / 2, TJ);
@@ -115,15 +132,9 @@ static void launch_stencil(level_type *level, StencilArgs &A)
   A.low = HPGMG_DEV(level)->low;
   A.h2inv = 1.0 / (level->h * level->h);
   const int n = L.dim;
-  if (g_force_generic < 0) {
-    const char *e = getenv("HPGMG_B200_GENERIC_STENCIL");
-    g_force_generic = (e && atoi(e)) ? 1 : 0;
-    const char *as = getenv("HPGMG_B200_TILED_ASYNC");
-    if (as) g_tiled_async = atoi(as);
-    const char *kc = getenv("HPGMG_B200_KCHUNK");
-    if (kc) g_kchunk_override = atoi(kc);
-  }
+  stencil_env();
   if (OP != OP_REBUILD && !g_force_generic) {
+    if (n == 64 && g_tile32) { launch_tiled<OP, 32, 8>(A); return; }
     if (n % 64 == 0) { launch_tiled<OP, 64, 8>(A); return; }
   }
   dim3 block(n >= 32 ? 32 : (n >= 16 ? 16 : 8), n >= 32 ? 4 : 4, n >= 32 ? 2 : 4);
@@ -178,6 +189,117 @@ extern "C" void hpgmg_b200_gsrb_sweep(level_type *level, int src_id, int dst_id,
   launch_stencil<OP_GSRB>(level, A);
 }
 
+/* ---- small levels: a whole smooth() as ONE persistent kernel ---------------------------------------- */
+/* EXPERIMENT, off by default (HPGMG_B200_PERSISTENT_SMOOTH=1): measured 8.34 ms vs 8.15 ms per `7 8` solve --
+ * inside a CUDA graph the 12 launches it replaces are cheaper than its 11 grid barriers at 8 warps/SM.
+ * Boxes of <= 32^3 cells that live entirely on this GPU: the 6 x (ghost fill, sweep) of a smooth are
+ * microsecond-sized.  One cooperative kernel (all blocks co-resident) runs the 12 phases back to back,
+ * separated by a grid-wide barrier; a thread owns an
+ * i-pair of cells, so on a red-black sweep every lane evaluates exactly one stencil.  Same device
+ * bodies as the stand-alone kernels (fill.cuh, stencil.cuh): same bits. */
+#include "fill.cuh"
+
+struct SmoothArgs {
+  DLevel L;
+  const int *low;
+  const FillCopy *copies;  int ncopies;
+  const FillBC *bc;        int nbc;
+  int x_id, rhs_id, version, cheby;
+  double b, h2inv;
+  double c1[6], c2[6];
+  unsigned int *barrier;                           /* zeroed before the launch */
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &generation)
+{
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    generation++;
+    atomicAdd(bar, 1u);
+    while (*(volatile unsigned int *)bar < generation * gridDim.x) { }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 1) smooth_persistent_kernel(const SmoothArgs A)
+{
+  PDL_WAIT();
+  const DLevel &L = A.L;
+  const int n = L.dim, hn = n / 2, jS = L.jStride, kS = L.kStride;
+  const int gthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int pairs_per_box = hn * n * n, pairs = pairs_per_box * L.nboxes;
+  unsigned int generation = 0;
+  for (int s = 0; s < 6; s++) {
+    const int src = (s & 1) ? VECTOR_TEMP : A.x_id, dst = (s & 1) ? A.x_id : VECTOR_TEMP;
+    for (int t = gtid; t < A.ncopies + A.nbc; t += gthreads) fill_items(L, src, t, A.copies, A.ncopies, A.bc, A.nbc, A.version);
+    grid_barrier(A.barrier, generation);
+    for (int q = gtid; q < pairs; q += gthreads) {
+      const int box = q / pairs_per_box, c = q - box * pairs_per_box;
+      const int p = c % hn, j = (c / hn) % n, k = c / (hn * n);
+      const int ijk = 2 * p + j * jS + k * kS;
+      const double *x = L.vec(box, src) + ijk;
+      const double *bi = L.vec(box, VECTOR_BETA_I) + ijk, *bj = L.vec(box, VECTOR_BETA_J) + ijk, *bk = L.vec(box, VECTOR_BETA_K) + ijk;
+      const double2 rhs2 = *reinterpret_cast<const double2 *>(L.vec(box, A.rhs_id) + ijk);
+      const double2 dinv2 = *reinterpret_cast<const double2 *>(L.vec(box, VECTOR_DINV) + ijk);
+      double2 *out = reinterpret_cast<double2 *>(L.vec(box, dst) + ijk);
+      if (!A.cheby) {
+        const int color000 = (A.low[3 * box] ^ A.low[3 * box + 1] ^ A.low[3 * box + 2] ^ s) & 1;
+        const int a = (j ^ k ^ color000) & 1;                 /* the active cell of the pair */
+        const double Ax = fv4_apply_op(x + a, bi + a, bj + a, bk + a, jS, kS, A.b, A.h2inv);
+        const double xnew = x[a] + (a ? dinv2.y : dinv2.x) * ((a ? rhs2.y : rhs2.x) - Ax);
+        const double xo = x[1 - a];
+        *out = a ? make_double2(xo, xnew) : make_double2(xnew, xo);
+      } else {
+        const double2 xm = *out;                               /* x_nm1 aliases x_np1 (chebyshev.c:75-80) */
+        const double Ax0 = fv4_apply_op(x, bi, bj, bk, jS, kS, A.b, A.h2inv);
+        const double Ax1 = fv4_apply_op(x + 1, bi + 1, bj + 1, bk + 1, jS, kS, A.b, A.h2inv);
+        const double r0 = x[0] + A.c1[s] * (x[0] - xm.x) + A.c2[s] * dinv2.x * (rhs2.x - Ax0);
+        const double r1 = x[1] + A.c1[s] * (x[1] - xm.y) + A.c2[s] * dinv2.y * (rhs2.y - Ax1);
+        *out = make_double2(r0, r1);
+      }
+    }
+    if (s < 5) grid_barrier(A.barrier, generation);
+  }
+}
+
+static unsigned int *g_smooth_barrier = NULL;
+
+/* 1 if the smooth was enqueued as the persistent kernel */
+static int smooth_persistent(level_type *level, int x_id, int rhs_id, double a, double b)
+{
+  hpgmg_device_level *D = HPGMG_DEV(level);
+  const DLevel &L = D->L;
+  stencil_env();
+  if (!g_persistent_smooth || L.nboxes == 0 || (L.dim & 1) || L.dim > 32 || L.dim < 4) return 0;
+  if (level->boundary_condition.type != BC_DIRICHLET || level->box_ghosts != 2 || D->fill_nvec != level->numVectors) return 0;
+  const communicator_type *C = &level->exchange_ghosts[STENCIL_SHAPE_NO_CORNERS];
+  if (C->num_sends > 0 || C->num_recvs > 0) return 0;                       /* neighbours on other GPUs: the kernel-per-phase path */
+  if (!g_smooth_barrier) g_smooth_barrier = reinterpret_cast<unsigned int *>(hpgmg_rt_scalar_slots() + HPGMG_SLOT_BARRIER);   /* preallocated: no cudaMalloc during capture */
+  const FillTable &T = D->fill[STENCIL_SHAPE_NO_CORNERS];
+  SmoothArgs A;
+  memset(&A, 0, sizeof(A));
+  A.L = L;  A.low = D->low;
+  A.copies = T.copies;  A.ncopies = T.ncopies;  A.bc = T.bc;  A.nbc = T.nbc;
+  A.x_id = x_id;  A.rhs_id = rhs_id;  A.version = 4;  A.b = b;  A.h2inv = 1.0 / (level->h * level->h);
+  A.cheby = hpgmg_rt_smoother() == HPGMG_SMOOTHER_CHEBY;
+  if (A.cheby) {                                                            /* chebyshev.c:22-40 */
+    double beta = 1.000 * level->dominant_eigenvalue_of_DinvA, alpha = 0.125000 * beta;
+    double theta = 0.5 * (beta + alpha), delta = 0.5 * (beta - alpha), sigma = theta / delta, rho_n = 1 / sigma;
+    A.c1[0] = 0.0;  A.c2[0] = 1 / theta;
+    for (int s = 1; s < 6; s++) { double rho_nm1 = rho_n; rho_n = 1.0 / (2.0 * sigma - rho_nm1); A.c1[s] = rho_n * rho_nm1; A.c2[s] = rho_n * 2.0 / delta; }
+  }
+  A.barrier = g_smooth_barrier;
+  const int pairs = (L.dim / 2) * L.dim * L.dim * L.nboxes;
+  int blocks = (pairs + 255) / 256;
+  if (blocks > 148) blocks = 148;                                           /* one block per SM: all co-resident */
+  CUDA_CHECK(cudaMemsetAsync(g_smooth_barrier, 0, sizeof(unsigned int), g_stream));
+  hpgmg_launch_cooperative("smooth_persistent_kernel", smooth_persistent_kernel, dim3(blocks), dim3(256), 0, A);
+  (void)a;
+  return 1;
+}
+
 static void smooth_chebyshev(level_type *level, int x_id, int rhs_id, double a, double b)
 {
   enum { DEGREE = 6 };                               /* CHEBYSHEV_DEGREE (operators.fv4.c:184) */
@@ -211,6 +333,7 @@ static void smooth_chebyshev(level_type *level, int x_id, int rhs_id, double a, 
 
 extern "C" void smooth(level_type *level, int x_id, int rhs_id, double a, double b)
 {
+  if (smooth_persistent(level, x_id, rhs_id, a, b)) return;
   if (hpgmg_rt_smoother() == HPGMG_SMOOTHER_CHEBY) smooth_chebyshev(level, x_id, rhs_id, a, b);
   else smooth_gsrb(level, x_id, rhs_id, a, b);
 }

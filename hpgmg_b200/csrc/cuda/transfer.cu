@@ -52,6 +52,30 @@ __global__ void __launch_bounds__(128) restriction_kernel(const DLevel Lc, const
   }
 }
 
+/* cell restriction of box -> box entries: one thread per coarse cell, the 2x2x2 children read as four
+ * 16-byte pairs (same summation order as restriction.c:54-57) */
+__global__ void __launch_bounds__(256) restriction_cell_kernel(const DLevel Lc, const int id_c, const DLevel Lf, const int id_f,
+                                                               const blockCopy_type *__restrict__ blocks)
+{
+  PDL_WAIT();
+  const blockCopy_type B = blocks[blockIdx.x];
+  const int di = B.dim.i, dj = B.dim.j, cells = di * dj * B.dim.k;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= cells) return;
+  const int i = c % di, j = (c / di) % dj, k = c / (di * dj);
+  const int rj = Lf.jStride, rk = Lf.kStride;
+  const double *r = Lf.vec(B.read.box, id_f) + (B.read.i + 2 * i) + (B.read.j + 2 * j) * rj + (B.read.k + 2 * k) * rk;
+  double v;
+  if ((B.read.i & 1) == 0) {
+    const double2 a = *reinterpret_cast<const double2 *>(r), b = *reinterpret_cast<const double2 *>(r + rj);
+    const double2 c2 = *reinterpret_cast<const double2 *>(r + rk), d = *reinterpret_cast<const double2 *>(r + rj + rk);
+    v = (a.x + a.y + b.x + b.y + c2.x + c2.y + d.x + d.y) * 0.125;
+  } else {
+    v = (r[0] + r[1] + r[rj] + r[1 + rj] + r[rk] + r[1 + rk] + r[rj + rk] + r[1 + rj + rk]) * 0.125;
+  }
+  Lc.vec(B.write.box, id_c)[(B.write.i + i) + (B.write.j + j) * Lc.jStride + (B.write.k + k) * Lc.kStride] = v;
+}
+
 static void run_restriction_list(level_type *level_c, int id_c, level_type *level_f, int id_f, const DList &list, int type)
 {
   if (list.n <= 0) return;
@@ -68,7 +92,13 @@ extern "C" void restriction(level_type *level_c, int id_c, level_type *level_f, 
     run_restriction_list(level_c, id_c, level_f, id_f, Df->restriction[restrictionType][0], restrictionType);   /* pack */
     hpgmg_comm_transfer(level_f, Cf, level_c, Cc, 0x5);
   }
-  run_restriction_list(level_c, id_c, level_f, id_f, Df->restriction[restrictionType][1], restrictionType);     /* local */
+  const DList &local = Df->restriction[restrictionType][1];
+  if (restrictionType == RESTRICT_CELL && local.n > 0) {                                                        /* local, fast path */
+    const int half = level_f->box_dim / 2;
+    const int cells = half * (half < BLOCKCOPY_TILE_J ? half : BLOCKCOPY_TILE_J) * (half < BLOCKCOPY_TILE_K ? half : BLOCKCOPY_TILE_K);
+    LAUNCH(restriction_cell_kernel, dim3(local.n, (cells + 255) / 256), 256, 0, dl_of(level_c), id_c, dl_of(level_f), id_f, local.blocks);
+  } else
+    run_restriction_list(level_c, id_c, level_f, id_f, local, restrictionType);                                 /* local */
   if (remote) {
     hpgmg_comm_transfer_wait(level_f, Cf, level_c, Cc);
     hpgmg_run_copy_list(Dc->L, id_c, Dc->restriction[restrictionType][2]);                                      /* unpack */
@@ -148,6 +178,78 @@ __global__ void __launch_bounds__(128) interpolation_kernel(const DLevel Lf, con
   }
 }
 
+/* The same arithmetic for box -> box entries, staged through shared memory: a thread block takes a
+ * 32 x 4 x 2 sub-tile of coarse cells of one list entry, loads the tile plus its W/2-cell halo once
+ * (instead of every thread fetching 27 / 125 overlapping values through L1), and writes each fine
+ * i-pair as one 16-byte access. */
+template <int W>
+__global__ void __launch_bounds__(256) interpolation_tiled_kernel(const DLevel Lf, const int id_f, const double prescale,
+                                                                  const DLevel Lc, const int id_c,
+                                                                  const blockCopy_type *__restrict__ blocks)
+{
+  PDL_WAIT();
+  constexpr int R = W / 2, CI = 32, CJ = 4, CK = 2;
+  constexpr int SI = CI + 2 * R, SJ = CJ + 2 * R, SK = CK + 2 * R;
+  __shared__ double tile[SK][SJ][SI];
+  const blockCopy_type B = blocks[blockIdx.x];
+  const int di = B.dim.i, dj = B.dim.j, dk = B.dim.k;
+  const int ni = (di + CI - 1) / CI, nj = (dj + CJ - 1) / CJ;
+  const int ti0 = ((int)blockIdx.y % ni) * CI, tj0 = (((int)blockIdx.y / ni) % nj) * CJ, tk0 = ((int)blockIdx.y / (ni * nj)) * CK;
+  if (tk0 >= dk) return;
+  const int rj = Lc.jStride, rk = Lc.kStride, wj = Lf.jStride, wk = Lf.kStride;
+  const double *__restrict__ rd = Lc.vec(B.read.box, id_c) + (B.read.i + ti0 - R) + (B.read.j + tj0 - R) * rj + (B.read.k + tk0 - R) * rk;
+  const int tid = threadIdx.x + CI * (threadIdx.y + CJ * threadIdx.z);
+  /* only the part of the halo tile that some coarse cell of this sub-tile needs */
+  const int ei = min(CI, di - ti0) + 2 * R, ej = min(CJ, dj - tj0) + 2 * R, ek = min(CK, dk - tk0) + 2 * R;
+  for (int e = tid; e < SI * SJ * SK; e += CI * CJ * CK) {
+    const int i = e % SI, j = (e / SI) % SJ, k = e / (SI * SJ);
+    if (i < ei && j < ej && k < ek) tile[k][j][i] = rd[i + j * rj + k * rk];
+  }
+  __syncthreads();
+  const int ii = ti0 + threadIdx.x, jj = tj0 + threadIdx.y, kk = tk0 + threadIdx.z;
+  if (ii >= di || jj >= dj || kk >= dk) return;
+  const int cx = threadIdx.x + R, cy = threadIdx.y + R, cz = threadIdx.z + R;
+  double fi[2][W][W];
+#pragma unroll
+  for (int K = 0; K < W; K++)
+#pragma unroll
+  for (int J = 0; J < W; J++) {
+    const double *p = &tile[cz + K - R][cy + J - R][cx];
+    if constexpr (W == 3) prolong3(p[-1], p[0], p[1], fi[0][J][K], fi[1][J][K]);
+    else                  prolong5(p[-2], p[-1], p[0], p[1], p[2], fi[0][J][K], fi[1][J][K]);
+  }
+  double fj[2][2][W];
+#pragma unroll
+  for (int K = 0; K < W; K++)
+#pragma unroll
+  for (int I = 0; I < 2; I++) {
+    if constexpr (W == 3) prolong3(fi[I][0][K], fi[I][1][K], fi[I][2][K], fj[I][0][K], fj[I][1][K]);
+    else                  prolong5(fi[I][0][K], fi[I][1][K], fi[I][2][K], fi[I][3][K], fi[I][W - 1][K], fj[I][0][K], fj[I][1][K]);
+  }
+  double *w = Lf.vec(B.write.box, id_f) + (2 * ii + B.write.i) + (2 * jj + B.write.j) * wj + (2 * kk + B.write.k) * wk;
+  const bool vec2 = (((B.write.i) & 1) == 0);             /* fine i-pairs are 16-byte aligned when the entry starts on an even cell */
+#pragma unroll
+  for (int J = 0; J < 2; J++) {
+    double lo[2], hi[2];
+#pragma unroll
+    for (int I = 0; I < 2; I++) {
+      if constexpr (W == 3) prolong3(fj[I][J][0], fj[I][J][1], fj[I][J][2], lo[I], hi[I]);
+      else                  prolong5(fj[I][J][0], fj[I][J][1], fj[I][J][2], fj[I][J][3], fj[I][J][W - 1], lo[I], hi[I]);
+    }
+    double *w0 = w + J * wj;
+    if (vec2) {
+      double2 a = *reinterpret_cast<double2 *>(w0), b2 = *reinterpret_cast<double2 *>(w0 + wk);
+      a.x = prescale * a.x + lo[0];   a.y = prescale * a.y + lo[1];
+      b2.x = prescale * b2.x + hi[0]; b2.y = prescale * b2.y + hi[1];
+      *reinterpret_cast<double2 *>(w0) = a;
+      *reinterpret_cast<double2 *>(w0 + wk) = b2;
+    } else {
+      w0[0] = prescale * w0[0] + lo[0];        w0[1] = prescale * w0[1] + lo[1];
+      w0[wk] = prescale * w0[wk] + hi[0];      w0[wk + 1] = prescale * w0[wk + 1] + hi[1];
+    }
+  }
+}
+
 /* fine-level unpack of prolonged data received from another rank: write = prescale*write + recv
  * (IncrementBlock, blockCopy.c:108-156) */
 __global__ void __launch_bounds__(128) increment_blocks_kernel(const DLevel L, const int id, const double prescale, const blockCopy_type *__restrict__ blocks)
@@ -183,7 +285,13 @@ static void interpolation_driver(level_type *level_f, int id_f, double prescale_
     hpgmg_comm_transfer(level_c, Cc, level_f, Cf, 0x7);
   }
   const DList &local = Dc->interpolation[1];
-  if (local.n > 0) LAUNCH(interpolation_kernel<W>, local.n, 128, 0, Df->L, id_f, prescale_f, Dc->L, id_c, local.blocks, 0);
+  if (local.n > 0) {
+    /* local entries are box -> box tiles of at most 10000 x 8 x 8 coarse cells (mg.c:274-277) */
+    const int half = level_f->box_dim / 2;
+    const int di = half, dj = half < BLOCKCOPY_TILE_J ? half : BLOCKCOPY_TILE_J, dk = half < BLOCKCOPY_TILE_K ? half : BLOCKCOPY_TILE_K;
+    const int subtiles = ((di + 31) / 32) * ((dj + 3) / 4) * ((dk + 1) / 2);
+    LAUNCH(interpolation_tiled_kernel<W>, dim3(local.n, subtiles), dim3(32, 4, 2), 0, Df->L, id_f, prescale_f, Dc->L, id_c, local.blocks);
+  }
   if (remote) {
     hpgmg_comm_transfer_wait(level_c, Cc, level_f, Cf);
     const DList &unpack = Df->interpolation[2];

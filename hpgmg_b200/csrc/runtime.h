@@ -59,6 +59,7 @@ void    hpgmg_rt_read_scalars(double *host, int first, int count); /* sync + cop
 #define HPGMG_SLOT_NORM_R   1
 #define HPGMG_SLOT_KRYLOV   2   /* bottom-solver iterations of the current solve (as a double) */
 #define HPGMG_SLOT_SCRATCH  8
+#define HPGMG_SLOT_BARRIER  32  /* grid-barrier counter of the persistent smoother */
 
 /* async reductions that leave their result in a scalar slot (no host sync) */
 void hpgmg_norm_async(level_type *level, int id_a, int slot);
