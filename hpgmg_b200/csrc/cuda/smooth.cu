@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(const StencilArgs 
 #include "stencil_tiled.cuh"
 
 static int g_tiled_async = 1;
-static int g_force_generic = -1, g_kchunk_override = -1, g_tile32 = 0, g_min_chunk = 16, g_persistent_smooth = 0;
+static int g_force_generic = -1, g_kchunk_override = -1, g_tile32 = 0, g_min_chunk = 16, g_persistent_smooth = 0, g_pair_kernel = 1;
 
 static void stencil_env(void)
 {
@@ -91,6 +91,8 @@ static void stencil_env(void)
     if (t32) g_tile32 = atoi(t32);
     const char *mc = getenv("HPGMG_B200_MIN_CHUNK");
     if (mc) g_min_chunk = atoi(mc);
+    const char *pk = getenv("HPGMG_B200_PAIR_KERNEL");
+    if (pk) g_pair_kernel = atoi(pk);
     const char *ps = getenv("HPGMG_B200_PERSISTENT_SMOOTH");
     if (ps) g_persistent_smooth = atoi(ps);
     const char *as = getenv("HPGMG_B200_TILED_ASYNC");
@@ -123,6 +125,50 @@ static void launch_tiled(const StencilArgs &A)
   else               LAUNCH((stencil_tiled_kernel<OP, TI, TJ, false>), grid, block, C::SMEM, A, kchunk);
 }
 
+/* Small even boxes (<= 32^3): one thread per i-PAIR of cells, straight from global memory through L1.
+ * On a GSRB sweep exactly one cell of the pair is active, so every lane evaluates one stencil (the
+ * per-cell kernel above idles half of each warp); results leave as 16-byte stores. */
+template <int OP>
+__global__ void __launch_bounds__(256) stencil_pair_kernel(const StencilArgs A)
+{
+  PDL_WAIT();
+  const DLevel &L = A.L;
+  const int n = L.dim, hn = n >> 1;
+  const int ktiles = (n + blockDim.z - 1) / blockDim.z;
+  const int box = blockIdx.z / ktiles;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  const int k = (blockIdx.z % ktiles) * blockDim.z + threadIdx.z;
+  if (p >= hn || j >= n || k >= n) return;
+  const int jS = L.jStride, kS = L.kStride;
+  const int ijk = 2 * p + j * jS + k * kS;
+  const double *__restrict__ x  = L.vec(box, A.x_id) + ijk;
+  const double *__restrict__ bi = L.vec(box, VECTOR_BETA_I) + ijk;
+  const double *__restrict__ bj = L.vec(box, VECTOR_BETA_J) + ijk;
+  const double *__restrict__ bk = L.vec(box, VECTOR_BETA_K) + ijk;
+  double2 *out = reinterpret_cast<double2 *>(L.vec(box, A.out_id) + ijk);
+  if (OP == OP_GSRB) {
+    const int color000 = (A.low[3 * box] ^ A.low[3 * box + 1] ^ A.low[3 * box + 2] ^ A.sweep) & 1;
+    const int a = (j ^ k ^ color000) & 1;                     /* the active cell of the pair */
+    const double2 rhs2 = *reinterpret_cast<const double2 *>(L.vec(box, A.rhs_id) + ijk);
+    const double2 dinv2 = *reinterpret_cast<const double2 *>(L.vec(box, VECTOR_DINV) + ijk);
+    const double Ax = fv4_apply_op(x + a, bi + a, bj + a, bk + a, jS, kS, A.b, A.h2inv);
+    const double xnew = x[a] + (a ? dinv2.y : dinv2.x) * ((a ? rhs2.y : rhs2.x) - Ax);
+    const double xo = x[1 - a];
+    *out = a ? make_double2(xo, xnew) : make_double2(xnew, xo);
+    return;
+  }
+  const double Ax0 = fv4_apply_op(x, bi, bj, bk, jS, kS, A.b, A.h2inv);
+  const double Ax1 = fv4_apply_op(x + 1, bi + 1, bj + 1, bk + 1, jS, kS, A.b, A.h2inv);
+  if (OP == OP_APPLY) { *out = make_double2(Ax0, Ax1); return; }
+  const double2 rhs2 = *reinterpret_cast<const double2 *>(L.vec(box, A.rhs_id) + ijk);
+  if (OP == OP_RESIDUAL) { *out = make_double2(rhs2.x - Ax0, rhs2.y - Ax1); return; }
+  const double2 dinv2 = *reinterpret_cast<const double2 *>(L.vec(box, VECTOR_DINV) + ijk);   /* OP_CHEBY */
+  const double2 xm = *reinterpret_cast<const double2 *>(L.vec(box, A.xm1_id) + ijk);
+  *out = make_double2(x[0] + A.c1 * (x[0] - xm.x) + A.c2 * dinv2.x * (rhs2.x - Ax0),
+                      x[1] + A.c1 * (x[1] - xm.y) + A.c2 * dinv2.y * (rhs2.y - Ax1));
+}
+
 template <int OP>
 static void launch_stencil(level_type *level, StencilArgs &A)
 {
@@ -136,6 +182,15 @@ static void launch_stencil(level_type *level, StencilArgs &A)
   if (OP != OP_REBUILD && !g_force_generic) {
     if (n == 64 && g_tile32) { launch_tiled<OP, 32, 8>(A); return; }
     if (n % 64 == 0) { launch_tiled<OP, 64, 8>(A); return; }
+    if ((n & 1) == 0 && n >= 4 && g_pair_kernel) {
+      const int hn = n / 2;
+      dim3 block(hn >= 16 ? 16 : hn, n >= 8 ? 8 : n, hn >= 16 ? 2 : (n >= 8 ? 256 / (hn * 8) : 256 / (hn * n)));
+      if ((int)block.z > n) block.z = n;
+      const int ktiles = (n + block.z - 1) / block.z;
+      dim3 grid((hn + block.x - 1) / block.x, (n + block.y - 1) / block.y, ktiles * L.nboxes);
+      LAUNCH(stencil_pair_kernel<OP>, grid, block, 0, A);
+      return;
+    }
   }
   dim3 block(n >= 32 ? 32 : (n >= 16 ? 16 : 8), n >= 32 ? 4 : 4, n >= 32 ? 2 : 4);
   const int ktiles = (n + block.z - 1) / block.z;
