@@ -72,9 +72,47 @@ __device__ static void c_fill_ghosts(const CoarseLevel &V, const int id, const b
   __syncthreads();
 }
 
-/* one sweep / residual over every cell of every box.  mode: 0 GSRB sweep s, 1 Chebyshev sweep s, 2 residual */
+/* one sweep / residual over every cell of every box.  mode: 0 GSRB sweep s, 1 Chebyshev sweep s, 2 residual.
+ * Even box sizes: a thread owns an i-pair (GSRB: exactly one active cell per pair, so no lane idles). */
+__device__ static void c_stencil_pairs(const CoarseLevel &V, const int mode, const int src, const int dst, const int rhs_id, const int s, const double b)
+{
+  const DLevel &L = V.L;
+  const int n = L.dim, jS = L.jStride, kS = L.kStride;
+  const int hn = n >> 1, per_box = hn * n * n, total = per_box * L.nboxes;
+  for (int q = threadIdx.x; q < total; q += blockDim.x) {
+    const int box = q / per_box, c = q - box * per_box;
+    const int p = c % hn, j = (c / hn) % n, k = c / (hn * n);
+    const int ijk = 2 * p + j * jS + k * kS;
+    const double *x = L.vec(box, src) + ijk;
+    const double *bi = L.vec(box, VECTOR_BETA_I) + ijk, *bj = L.vec(box, VECTOR_BETA_J) + ijk, *bk = L.vec(box, VECTOR_BETA_K) + ijk;
+    const double *rhs = L.vec(box, rhs_id) + ijk;
+    double *out = L.vec(box, dst) + ijk;
+    if (mode == 0) {
+      const int color000 = (V.low[3 * box] ^ V.low[3 * box + 1] ^ V.low[3 * box + 2] ^ s) & 1;
+      const int a = (j ^ k ^ color000) & 1;
+      const double Ax = fv4_apply_op(x + a, bi + a, bj + a, bk + a, jS, kS, b, V.h2inv);
+      const double xnew = x[a] + L.vec(box, VECTOR_DINV)[ijk + a] * (rhs[a] - Ax);
+      out[1 - a] = x[1 - a];
+      out[a] = xnew;
+    } else {
+      const double Ax0 = fv4_apply_op(x, bi, bj, bk, jS, kS, b, V.h2inv);
+      const double Ax1 = fv4_apply_op(x + 1, bi + 1, bj + 1, bk + 1, jS, kS, b, V.h2inv);
+      if (mode == 2) { out[0] = rhs[0] - Ax0; out[1] = rhs[1] - Ax1; }
+      else {
+        const double *dinv = L.vec(box, VECTOR_DINV) + ijk;
+        const double r0 = x[0] + V.c1[s] * (x[0] - out[0]) + V.c2[s] * dinv[0] * (rhs[0] - Ax0);
+        const double r1 = x[1] + V.c1[s] * (x[1] - out[1]) + V.c2[s] * dinv[1] * (rhs[1] - Ax1);
+        out[0] = r0;  out[1] = r1;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+/* the same, one thread per cell (odd box sizes) */
 __device__ static void c_stencil(const CoarseLevel &V, const int mode, const int src, const int dst, const int rhs_id, const int s, const double b)
 {
+  if ((V.L.dim & 1) == 0) { c_stencil_pairs(V, mode, src, dst, rhs_id, s, b); return; }
   const DLevel &L = V.L;
   const int n = L.dim, cells = n * n * n, total = cells * L.nboxes;
   for (int q = threadIdx.x; q < total; q += blockDim.x) {
