@@ -180,7 +180,7 @@ static void launch_stencil(level_type *level, StencilArgs &A)
   const int n = L.dim;
   stencil_env();
   if (OP != OP_REBUILD && !g_force_generic) {
-    if (n == 64 && g_tile32) { launch_tiled<OP, 32, 8>(A); return; }
+    if (n % 32 == 0 && n >= 64 && (g_tile32 == 2 || (g_tile32 == 1 && n == 64))) { launch_tiled<OP, 32, 8>(A); return; }
     if (n % 64 == 0) { launch_tiled<OP, 64, 8>(A); return; }
     if ((n & 1) == 0 && n >= 4 && g_pair_kernel) {
       const int hn = n / 2;

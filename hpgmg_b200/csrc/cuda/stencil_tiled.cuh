@@ -147,19 +147,29 @@ __global__ void __launch_bounds__((TI / 2) * TJ, 2) stencil_tiled_kernel(const S
   if (ASYNC) { ix.init(jS, tid); ib.init(jS, tid); }
 
   /* prologue: x planes k0-2..k0+2, beta_i/j planes k0-1..k0+1, beta_k planes k0, k0+1 */
-  for (int kk = k0 - 2; kk <= k0 + 2; kk++) {
-    plane_fetch<C::NT, C::HW, C::XE, C::XN>(px, gx + kk * kS, jS, tid);
-    plane_park<C::NT, C::HW, C::XE, C::XN>(px, xs + ((kk + 2) % C::XP) * C::XPL, tid);
-  }
-  for (int kk = k0 - 1; kk <= k0 + 1; kk++) {
-    plane_fetch<C::NT, C::HW, C::BE, C::BN>(pbi, gbi + kk * kS, jS, tid);
-    plane_fetch<C::NT, C::HW, C::BE, C::BN>(pbj, gbj + kk * kS, jS, tid);
-    plane_park<C::NT, C::HW, C::BE, C::BN>(pbi, bis + ((kk + 1) % C::BP) * C::BPL, tid);
-    plane_park<C::NT, C::HW, C::BE, C::BN>(pbj, bjs + ((kk + 1) % C::BP) * C::BPL, tid);
-  }
-  for (int kk = k0; kk <= k0 + 1; kk++) {
-    plane_fetch<C::NT, C::HW, C::BE, C::BN>(pbk, gbk + kk * kS, jS, tid);
-    plane_park<C::NT, C::HW, C::BE, C::BN>(pbk, bks + (kk % C::KP) * C::BPL, tid);
+  if (ASYNC) {                                        /* all 13 planes in flight at once: one memory latency, not thirteen */
+    for (int kk = k0 - 2; kk <= k0 + 2; kk++) ix.fetch_async(gx + kk * kS, xs + ((kk + 2) % C::XP) * C::XPL);
+    for (int kk = k0 - 1; kk <= k0 + 1; kk++) {
+      ib.fetch_async(gbi + kk * kS, bis + ((kk + 1) % C::BP) * C::BPL);
+      ib.fetch_async(gbj + kk * kS, bjs + ((kk + 1) % C::BP) * C::BPL);
+    }
+    for (int kk = k0; kk <= k0 + 1; kk++) ib.fetch_async(gbk + kk * kS, bks + (kk % C::KP) * C::BPL);
+    cp_async_wait_all();
+  } else {
+    for (int kk = k0 - 2; kk <= k0 + 2; kk++) {
+      plane_fetch<C::NT, C::HW, C::XE, C::XN>(px, gx + kk * kS, jS, tid);
+      plane_park<C::NT, C::HW, C::XE, C::XN>(px, xs + ((kk + 2) % C::XP) * C::XPL, tid);
+    }
+    for (int kk = k0 - 1; kk <= k0 + 1; kk++) {
+      plane_fetch<C::NT, C::HW, C::BE, C::BN>(pbi, gbi + kk * kS, jS, tid);
+      plane_fetch<C::NT, C::HW, C::BE, C::BN>(pbj, gbj + kk * kS, jS, tid);
+      plane_park<C::NT, C::HW, C::BE, C::BN>(pbi, bis + ((kk + 1) % C::BP) * C::BPL, tid);
+      plane_park<C::NT, C::HW, C::BE, C::BN>(pbj, bjs + ((kk + 1) % C::BP) * C::BPL, tid);
+    }
+    for (int kk = k0; kk <= k0 + 1; kk++) {
+      plane_fetch<C::NT, C::HW, C::BE, C::BN>(pbk, gbk + kk * kS, jS, tid);
+      plane_park<C::NT, C::HW, C::BE, C::BN>(pbk, bks + (kk % C::KP) * C::BPL, tid);
+    }
   }
   __syncthreads();
 
@@ -171,8 +181,14 @@ __global__ void __launch_bounds__((TI / 2) * TJ, 2) stencil_tiled_kernel(const S
   const double *g_xm1 = (OP == OP_CHEBY) ? L.vec(box, A.xm1_id) + cell : nullptr;
   double *g_out = L.vec(box, A.out_id) + cell;
 
+  /* point-wise operands (rhs, Dinv, x_{n-1}) are read one plane ahead into registers */
+  double2 rhs_n = make_double2(0.0, 0.0), dinv_n = make_double2(0.0, 0.0), xm_n = make_double2(0.0, 0.0);
+  if (OP != OP_APPLY) rhs_n = *reinterpret_cast<const double2 *>(g_rhs + k0 * kS);
+  if (OP == OP_GSRB || OP == OP_CHEBY) dinv_n = *reinterpret_cast<const double2 *>(g_dinv + k0 * kS);
+  if (OP == OP_CHEBY) xm_n = *reinterpret_cast<const double2 *>(g_xm1 + k0 * kS);
+
   for (int k = k0; k < k1; k++) {
-    /* ---- issue the loads of the next planes and of this plane's point-wise operands ---- */
+    /* ---- issue the loads of the next planes and of the next plane's point-wise operands ---- */
     const bool more_x = (k + 3 <= k1 + 1), more_b = (k + 2 <= k1);
     if (ASYNC) {                                      /* straight into the spare ring slots, no registers */
       if (more_x) ix.fetch_async(gx + (k + 3) * kS, xs + ((k + 5) % C::XP) * C::XPL);
@@ -189,10 +205,12 @@ __global__ void __launch_bounds__((TI / 2) * TJ, 2) stencil_tiled_kernel(const S
         plane_fetch<C::NT, C::HW, C::BE, C::BN>(pbk, gbk + (k + 2) * kS, jS, tid);
       }
     }
-    double2 rhs2 = make_double2(0.0, 0.0), dinv2 = make_double2(0.0, 0.0), xm2 = make_double2(0.0, 0.0);
-    if (OP != OP_APPLY) rhs2 = *reinterpret_cast<const double2 *>(g_rhs + k * kS);
-    if (OP == OP_GSRB || OP == OP_CHEBY) dinv2 = *reinterpret_cast<const double2 *>(g_dinv + k * kS);
-    if (OP == OP_CHEBY) xm2 = *reinterpret_cast<const double2 *>(g_xm1 + k * kS);
+    const double2 rhs2 = rhs_n, dinv2 = dinv_n, xm2 = xm_n;
+    if (k + 1 < k1) {
+      if (OP != OP_APPLY) rhs_n = *reinterpret_cast<const double2 *>(g_rhs + (k + 1) * kS);
+      if (OP == OP_GSRB || OP == OP_CHEBY) dinv_n = *reinterpret_cast<const double2 *>(g_dinv + (k + 1) * kS);
+      if (OP == OP_CHEBY) xm_n = *reinterpret_cast<const double2 *>(g_xm1 + (k + 1) * kS);
+    }
 
     /* ---- compute plane k from shared memory ---- */
     TileLoader<C::W, -2, 5> X;
