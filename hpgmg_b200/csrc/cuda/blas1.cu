@@ -90,23 +90,23 @@ static void launch_blas1(level_type *level, BlasArgs &A)
 }
 
 extern "C" void zero_vector(level_type *level, int id_a)
-{ BlasArgs A = {}; A.c = id_a; launch_blas1<B_ZERO>(level, A); }
+{ BlasArgs A = {}; ProfileScope prof_(&level->timers.blas1); A.c = id_a; launch_blas1<B_ZERO>(level, A); }
 extern "C" void init_vector(level_type *level, int id_a, double scalar)
-{ BlasArgs A = {}; A.c = id_a; A.sa = scalar; launch_blas1<B_INIT>(level, A); }
+{ BlasArgs A = {}; ProfileScope prof_(&level->timers.blas1); A.c = id_a; A.sa = scalar; launch_blas1<B_INIT>(level, A); }
 extern "C" void scale_vector(level_type *level, int id_c, double scale_a, int id_a)
-{ BlasArgs A = {}; A.c = id_c; A.a = id_a; A.sa = scale_a; launch_blas1<B_SCALE>(level, A); }
+{ BlasArgs A = {}; ProfileScope prof_(&level->timers.blas1); A.c = id_c; A.a = id_a; A.sa = scale_a; launch_blas1<B_SCALE>(level, A); }
 extern "C" void add_vectors(level_type *level, int id_c, double scale_a, int id_a, double scale_b, int id_b)
-{ BlasArgs A = {}; A.c = id_c; A.a = id_a; A.b = id_b; A.sa = scale_a; A.sb = scale_b; launch_blas1<B_ADD>(level, A); }
+{ BlasArgs A = {}; ProfileScope prof_(&level->timers.blas1); A.c = id_c; A.a = id_a; A.b = id_b; A.sa = scale_a; A.sb = scale_b; launch_blas1<B_ADD>(level, A); }
 extern "C" void mul_vectors(level_type *level, int id_c, double scale, int id_a, int id_b)
-{ BlasArgs A = {}; A.c = id_c; A.a = id_a; A.b = id_b; A.sa = scale; launch_blas1<B_MUL>(level, A); }
+{ BlasArgs A = {}; ProfileScope prof_(&level->timers.blas1); A.c = id_c; A.a = id_a; A.b = id_b; A.sa = scale; launch_blas1<B_MUL>(level, A); }
 extern "C" void invert_vector(level_type *level, int id_c, double scale_a, int id_a)
-{ BlasArgs A = {}; A.c = id_c; A.a = id_a; A.sa = scale_a; launch_blas1<B_INVERT>(level, A); }
+{ BlasArgs A = {}; ProfileScope prof_(&level->timers.blas1); A.c = id_c; A.a = id_a; A.sa = scale_a; launch_blas1<B_INVERT>(level, A); }
 extern "C" void shift_vector(level_type *level, int id_c, int id_a, double shift_a)
-{ BlasArgs A = {}; A.c = id_c; A.a = id_a; A.sa = shift_a; launch_blas1<B_SHIFT>(level, A); }
+{ BlasArgs A = {}; ProfileScope prof_(&level->timers.blas1); A.c = id_c; A.a = id_a; A.sa = shift_a; launch_blas1<B_SHIFT>(level, A); }
 extern "C" void color_vector(level_type *level, int id_a, int colors_in_each_dim, int icolor, int jcolor, int kcolor)
-{ BlasArgs A = {}; A.c = id_a; A.colors = colors_in_each_dim; A.ic = icolor; A.jc = jcolor; A.kc = kcolor; launch_blas1<B_COLOR>(level, A); }
+{ BlasArgs A = {}; ProfileScope prof_(&level->timers.blas1); A.c = id_a; A.colors = colors_in_each_dim; A.ic = icolor; A.jc = jcolor; A.kc = kcolor; launch_blas1<B_COLOR>(level, A); }
 extern "C" void random_vector(level_type *level, int id_a)
-{ BlasArgs A = {}; A.c = id_a; launch_blas1<B_RANDOM>(level, A); }
+{ BlasArgs A = {}; ProfileScope prof_(&level->timers.blas1); A.c = id_a; launch_blas1<B_RANDOM>(level, A); }
 
 /* ---- max norm ---------------------------------------------------------------------------------- */
 __global__ void __launch_bounds__(256) norm_kernel(const DLevel L, const int id, double *__restrict__ slot)
@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(256) norm_kernel(const DLevel L, const int id,
 
 extern "C" void hpgmg_norm_async(level_type *level, int id_a, int slot)
 {
+  ProfileScope prof_(&level->timers.blas1);
   double *s = hpgmg_rt_scalar_slots() + slot;
   CUDA_CHECK(cudaMemsetAsync(s, 0, sizeof(double), g_stream));
   g_launches++;
@@ -203,6 +204,7 @@ __global__ void ordered_total_kernel(const double *__restrict__ partials, const 
 
 static double ordered_sum(level_type *level, int id_a, int id_b, int mode)
 {
+  ProfileScope prof_(&level->timers.blas1);
   const int slot = HPGMG_SLOT_SCRATCH + 2;
   double *s = hpgmg_rt_scalar_slots() + slot;
   hpgmg_device_level *D = HPGMG_DEV(level);

@@ -117,6 +117,29 @@ struct hpgmg_device_level {
   int     ntiles;
 };
 
+/* per-operator timers of the reference (level->timers.*, e.g. gsrb.c:37,130): only when
+ * hpgmg_b200_profile_operators(1) is on; each bracket then synchronises the stream (graphs are off
+ * in that mode), so MGPrintTiming shows the same table as the reference. */
+struct ProfileScope {
+  double *field, *total;
+  double t0;
+  ProfileScope(double *f, double *tot = NULL) : field(NULL), total(tot), t0(0.0)
+  {
+    if (!hpgmg_rt_profile()) return;
+    field = f;
+    CUDA_CHECK(cudaStreamSynchronize(g_stream));
+    t0 = hpgmg_rt_wtime();
+  }
+  ~ProfileScope()
+  {
+    if (!field) return;
+    CUDA_CHECK(cudaStreamSynchronize(g_stream));
+    const double dt = hpgmg_rt_wtime() - t0;
+    *field += dt;
+    if (total) *total += dt;
+  }
+};
+
 static inline const DLevel &dl_of(const level_type *level) { return HPGMG_DEV(level)->L; }
 
 /* max over non-negative doubles through their bit pattern (IEEE order == unsigned integer order) */

@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(256) fill_ghosts_kernel(const FillArgs A)
  * separate list-walking kernels. */
 void hpgmg_fill_ghosts(level_type *level, int id, int shape, int bc_version)
 {
+  ProfileScope prof_(&level->timers.ghostZone_total);
   hpgmg_device_level *D = HPGMG_DEV(level);
   const FillTable &T = D->fill[shape];
   const bool dirichlet = level->boundary_condition.type == BC_DIRICHLET && bc_version != 0;
@@ -245,6 +246,7 @@ extern "C" void apply_BCs_v1(level_type *level, int x_id, int shape)
 
 extern "C" void apply_BCs_v2(level_type *level, int x_id, int shape)
 {
+  ProfileScope prof_(&level->timers.boundary_conditions);
   if (shape >= STENCIL_MAX_SHAPES) shape = STENCIL_SHAPE_BOX;
   if (level->boundary_condition.type == BC_PERIODIC) return;
   if (level->box_dim < 2) { apply_BCs_v1(level, x_id, shape); return; }
@@ -254,6 +256,7 @@ extern "C" void apply_BCs_v2(level_type *level, int x_id, int shape)
 
 extern "C" void apply_BCs_v4(level_type *level, int x_id, int shape)
 {
+  ProfileScope prof_(&level->timers.boundary_conditions);
   if (shape >= STENCIL_MAX_SHAPES) shape = STENCIL_SHAPE_BOX;
   if (level->boundary_condition.type == BC_PERIODIC) return;
   if (level->box_ghosts < 2) { fprintf(stderr, "called quartic BC's with only 1 ghost zone!!!\n"); exit(0); }

@@ -210,6 +210,7 @@ extern "C" int stencil_get_shape(void) { return STENCIL_SHAPE_NO_CORNERS; }
 
 extern "C" void apply_op(level_type *level, int Ax_id, int x_id, double a, double b)
 {
+  ProfileScope prof_(&level->timers.apply_op);
   fill_ghosts(level, x_id);
   StencilArgs A = {};
   A.x_id = x_id;  A.out_id = Ax_id;  A.a = a;  A.b = b;
@@ -218,6 +219,7 @@ extern "C" void apply_op(level_type *level, int Ax_id, int x_id, double a, doubl
 
 extern "C" void residual(level_type *level, int res_id, int x_id, int rhs_id, double a, double b)
 {
+  ProfileScope prof_(&level->timers.residual);
   fill_ghosts(level, x_id);
   StencilArgs A = {};
   A.x_id = x_id;  A.rhs_id = rhs_id;  A.out_id = res_id;  A.a = a;  A.b = b;
@@ -388,6 +390,7 @@ static void smooth_chebyshev(level_type *level, int x_id, int rhs_id, double a, 
 
 extern "C" void smooth(level_type *level, int x_id, int rhs_id, double a, double b)
 {
+  ProfileScope prof_(&level->timers.smooth);
   if (smooth_persistent(level, x_id, rhs_id, a, b)) return;
   if (hpgmg_rt_smoother() == HPGMG_SMOOTHER_CHEBY) smooth_chebyshev(level, x_id, rhs_id, a, b);
   else smooth_gsrb(level, x_id, rhs_id, a, b);
