@@ -124,6 +124,17 @@ extern "C" int hpgmg_rt_verbose(void) { return g_verbose; }
 extern "C" int hpgmg_rt_smoother(void) { return g_smoother; }
 extern "C" int hpgmg_rt_use_graphs(void) { return g_use_graphs; }
 extern "C" int hpgmg_rt_profile(void) { return g_profile; }
+extern "C" int hpgmg_rt_sm_count(void)
+{
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    CUDA_CHECK(cudaGetDevice(&dev));
+    CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
 extern "C" double hpgmg_rt_wtime(void)
 {
   struct timespec ts;

@@ -78,8 +78,10 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(const StencilArgs 
 }
 
 #include "stencil_tiled.cuh"
+#include "stencil_tma.cuh"
+#include <vector>
 
-static int g_tiled_async = 1;
+static int g_tiled_async = 1, g_tma = 1, g_tma_blocks = 0, g_tma32 = 0;
 static int g_force_generic = -1, g_kchunk_override = -1, g_tile32 = 0, g_min_chunk = 16, g_persistent_smooth = 0, g_pair_kernel = 1;
 
 static void stencil_env(void)
@@ -97,6 +99,12 @@ static void stencil_env(void)
     if (ps) g_persistent_smooth = atoi(ps);
     const char *as = getenv("HPGMG_B200_TILED_ASYNC");
     if (as) g_tiled_async = atoi(as);
+    const char *tm = getenv("HPGMG_B200_TMA");
+    if (tm) g_tma = atoi(tm);
+    const char *tb = getenv("HPGMG_B200_TMA_BLOCKS");
+    if (tb) g_tma_blocks = atoi(tb);
+    const char *t3 = getenv("HPGMG_B200_TMA32");
+    if (t3) g_tma32 = atoi(t3);
     const char *kc = getenv("HPGMG_B200_KCHUNK");
     if (kc) g_kchunk_override = atoi(kc);
   }
@@ -123,6 +131,69 @@ static void launch_tiled(const StencilArgs &A)
   dim3 grid(tiles, chunks, A.L.nboxes), block(TI / 2, TJ);
   if (g_tiled_async) LAUNCH((stencil_tiled_kernel<OP, TI, TJ, true>), grid, block, C::SMEM, A, kchunk);
   else               LAUNCH((stencil_tiled_kernel<OP, TI, TJ, false>), grid, block, C::SMEM, A, kchunk);
+}
+
+/* ---- TMA descriptors: the level slab [box*vector][k][j][i] as a rank-4 tensor, one (W x rows) tile per copy ---- */
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder(void)
+{
+  static EncodeTiledFn fn = NULL;
+  if (!fn) {
+    void *p = NULL;
+    cudaDriverEntryPointQueryResult q;
+    CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !p) { fprintf(stderr, "hpgmg_b200: cuTensorMapEncodeTiled is not available from this driver\n"); exit(1); }
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+struct TileMaps {
+  const double *base;  int nboxes, nvec, dim, w, xr, br;
+  CUtensorMap x, b;
+};
+static std::vector<TileMaps *> g_tile_maps;
+
+static const TileMaps *tile_maps(const DLevel &L, const int w, const int xr, const int br)
+{
+  for (size_t t = 0; t < g_tile_maps.size(); t++) {
+    const TileMaps *M = g_tile_maps[t];
+    if (M->base == L.base && M->nboxes == L.nboxes && M->nvec == L.nvec && M->dim == L.dim && M->w == w && M->xr == xr && M->br == br) return M;
+  }
+  TileMaps *M = NULL;
+  if (posix_memalign((void **)&M, 64, sizeof(TileMaps)) != 0) { fprintf(stderr, "hpgmg_b200: out of memory\n"); exit(1); }
+  M->base = L.base;  M->nboxes = L.nboxes;  M->nvec = L.nvec;  M->dim = L.dim;  M->w = w;  M->xr = xr;  M->br = br;
+  const cuuint64_t ext = (cuuint64_t)(L.dim + 2 * L.ghosts);
+  const cuuint64_t gdim[4] = { (cuuint64_t)L.jStride, ext, ext, (cuuint64_t)L.nboxes * (cuuint64_t)L.nvec };
+  const cuuint64_t gstride[3] = { (cuuint64_t)L.jStride * 8, (cuuint64_t)L.kStride * 8, (cuuint64_t)L.volume * 8 };
+  const cuuint32_t estride[4] = { 1, 1, 1, 1 };
+  for (int which = 0; which < 2; which++) {
+    const cuuint32_t box[4] = { (cuuint32_t)w, (cuuint32_t)(which ? br : xr), 1, 1 };
+    const CUresult rc = tensor_map_encoder()(which ? &M->b : &M->x, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void *)L.base, gdim, gstride, box, estride,
+                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) { fprintf(stderr, "hpgmg_b200: cuTensorMapEncodeTiled failed (%d) for dim %d jStride %d\n", (int)rc, L.dim, L.jStride); exit(1); }
+  }
+  g_tile_maps.push_back(M);
+  return M;
+}
+
+template <int OP, int TI, int TJ>
+static void launch_tma(const StencilArgs &A)
+{
+  typedef TmaCfg<TI, TJ> C;
+  static bool configured = false;
+  if (!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(stencil_tma_kernel<OP, TI, TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    configured = true;
+  }
+  const TileMaps *M = tile_maps(A.L, C::W, C::XR, C::BR);
+  const int n = A.L.dim;
+  const long long total = (long long)A.L.nboxes * (n / TI) * (n / TJ) * n;
+  /* persistent grid: every resident block slot (2 per SM) gets the same number of planes; keep >= 8 planes per block */
+  long long blocks = g_tma_blocks > 0 ? g_tma_blocks : 2LL * hpgmg_rt_sm_count();
+  if (blocks > total / 8) blocks = total / 8 > 0 ? total / 8 : 1;
+  LAUNCH((stencil_tma_kernel<OP, TI, TJ>), dim3((unsigned)blocks), dim3(C::NT), C::SMEM, A, M->x, M->b, total);
 }
 
 /* Small even boxes (<= 32^3): one thread per i-PAIR of cells, straight from global memory through L1.
@@ -181,6 +252,8 @@ static void launch_stencil(level_type *level, StencilArgs &A)
   stencil_env();
   if (OP != OP_REBUILD && !g_force_generic) {
     if (n % 32 == 0 && n >= 64 && (g_tile32 == 2 || (g_tile32 == 1 && n == 64))) { launch_tiled<OP, 32, 8>(A); return; }
+    if (n % 64 == 0 && g_tma) { launch_tma<OP, 64, 8>(A); return; }
+    if (n == 32 && g_tma32) { launch_tma<OP, 32, 8>(A); return; }
     if (n % 64 == 0) { launch_tiled<OP, 64, 8>(A); return; }
     if ((n & 1) == 0 && n >= 4 && g_pair_kernel) {
       const int hn = n / 2;

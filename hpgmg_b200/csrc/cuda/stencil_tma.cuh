@@ -1,0 +1,252 @@
+/*
+ * stencil_tma.cuh -- the operator kernels for boxes >= 32^3, Blackwell version: 2.5-D blocking, the
+ * halo tiles staged in shared memory by the TMA engine, a persistent grid with an even split of the
+ * (box, tile, k) work space.
+ *
+ * What it computes is what stencil_tiled.cuh computes (GSRB / Chebyshev / residual / apply_op on a
+ * TI x TJ column of cells marching along k; gsrb.c:41-129, chebyshev.c:51-97, residual.c:18-49,
+ * apply_op.c:18-47 with the macro of operators.fv4.c:87-114) -- the arithmetic is the same
+ * fv4_apply_op_at, hence the same bits.  What changed is everything around the arithmetic:
+ *
+ *  - staging: one elected thread issues cp.async.bulk.tensor (TMA) copies of whole (TI+4) x rows tiles
+ *    of x, beta_i, beta_j, beta_k for the next plane into ring buffers; completion is counted by an
+ *    mbarrier (complete_tx::bytes).  No LDGSTS / address arithmetic in the 8 compute warps (the
+ *    cp.async version spent 16 LDGSTS = 128 LSU cycles per warp and plane on it).
+ *  - layout: rows are stored as they are in memory (TMA cannot split parities).  Bank conflicts of the
+ *    stride-2 red-black accesses are avoided by the lane mapping instead: even lanes work on row r, odd
+ *    lanes on row r+1 of a row pair; the active cells of the two rows have opposite i-parity, so the 16
+ *    lanes of a half-warp touch 16 distinct 8-byte banks.
+ *  - addressing: a lane keeps ONE 32-bit shared address per ring slot (its active cell); every stencil
+ *    operand is a load at a compile-time offset from it (LDS [R+imm]).
+ *  - scheduling: grid = resident blocks (2 per SM); block b owns the planes [P*b/G, P*(b+1)/G) of the
+ *    linearised (box, tile, k) space, so all SMs finish together (the fixed k-chunk grid of the cp.async
+ *    kernel ran 1.73 waves on `7 8`).
+ */
+#ifndef HPGMG_B200_STENCIL_TMA_CUH
+#define HPGMG_B200_STENCIL_TMA_CUH
+
+#include <cuda.h>
+#include "stencil.cuh"
+
+template <int TI, int TJ>
+struct TmaCfg {
+  static constexpr int W = TI + 4;                 /* cells i0-2 .. i0+TI+1 of a row                      */
+  static constexpr int XR = TJ + 4;                /* x rows    j0-2 .. j0+TJ+1                           */
+  static constexpr int BR = TJ + 2;                /* beta rows j0-1 .. j0+TJ                             */
+  static constexpr int XP = 6, BP = 4, KP = 3;     /* ring depths: 5+1, 3+1, 2+1 planes                   */
+  static constexpr int NT = (TI / 2) * TJ;         /* threads: one per i-pair of cells                    */
+  static constexpr int XBYTES = XR * W * 8, BBYTES = BR * W * 8;          /* bytes one TMA copy delivers  */
+  static constexpr int XPB = (XBYTES + 127) / 128 * 128;                  /* slot pitch (TMA wants 128-B aligned destinations) */
+  static constexpr int BPB = (BBYTES + 127) / 128 * 128;
+  static constexpr int OFF_BI = XP * XPB, OFF_BJ = OFF_BI + BP * BPB, OFF_BK = OFF_BJ + BP * BPB, OFF_BAR = OFF_BK + KP * BPB;
+  static constexpr size_t SMEM = (size_t)OFF_BAR + 16 + 128;             /* + mbarrier + alignment slack */
+};
+
+/* ---- PTX wrappers ---------------------------------------------------------------------------------- */
+__device__ __forceinline__ double lds_f64(const unsigned a)
+{
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ void mbar_init(const unsigned bar, const unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(const unsigned bar, const unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(const unsigned bar, const unsigned parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra MBAR_DONE;\n"
+      "bra MBAR_WAIT;\n"
+      "MBAR_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+/* one (W x rows x 1 x 1) tile of the level slab viewed as [box*vector][k][j][i] */
+__device__ __forceinline__ void tma_load_4d(const unsigned dst, const CUtensorMap *map, const int c0, const int c1, const int c2, const int c3, const unsigned bar)
+{
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
+}
+
+/* shared-memory loader: a[d] is the byte address of the lane's active cell in the ring slot that holds
+ * plane k + DK0 + d; an operand at (di,dj,dk) is a load at a compile-time offset from it. */
+template <int W, int DK0, int NPLANES>
+struct SlotLoader {
+  unsigned a[NPLANES];
+  __device__ __forceinline__ double operator()(const int di, const int dj, const int dk) const
+  {
+    return lds_f64(a[dk - DK0] + (unsigned)((dj * W + di) * 8));
+  }
+};
+
+template <int OP, int TI, int TJ>
+__global__ void __launch_bounds__((TI / 2) * TJ, 2)
+stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b, const long long total_planes)
+{
+  typedef TmaCfg<TI, TJ> C;
+  extern __shared__ unsigned char smem_raw[];
+  const unsigned s0 = ((unsigned)__cvta_generic_to_shared(smem_raw) + 127u) & ~127u;
+  const unsigned xs = s0, bis = s0 + C::OFF_BI, bjs = s0 + C::OFF_BJ, bks = s0 + C::OFF_BK, bar = s0 + C::OFF_BAR;
+
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  PDL_WAIT();
+
+  const DLevel &L = A.L;
+  const int n = L.dim, jS = L.jStride, kS = L.kStride;
+  const int tiles_i = n / TI, tiles = tiles_i * (n / TJ);
+
+  /* lane -> (row, pair): even lanes row 2rp, odd lanes row 2rp+1; 16 consecutive pairs per warp */
+  constexpr int WPR = (TI / 2) / 16;                                /* warps per row pair */
+  const int warp = tid >> 5, lane = tid & 31;
+  const int r = 2 * (warp / WPR) + (lane & 1);
+  const int p = 16 * (warp % WPR) + (lane >> 1);
+  const unsigned lane_x = (unsigned)(((r + 2) * C::W + 2 + 2 * p) * 8);     /* even cell of the pair, x tile  */
+  const unsigned lane_b = (unsigned)(((r + 1) * C::W + 2 + 2 * p) * 8);     /* the same in the beta tiles     */
+
+  /* my share of the linearised (box, tile, k) space */
+  const long long lo = total_planes * (long long)blockIdx.x / (long long)gridDim.x;
+  const long long hi = total_planes * (long long)(blockIdx.x + 1) / (long long)gridDim.x;
+  unsigned phase = 0;
+
+  for (long long pos = lo; pos < hi;) {
+    const int col = (int)(pos / n);
+    const int k0 = (int)(pos - (long long)col * n);
+    const int k1 = (int)min((long long)n, (long long)k0 + (hi - pos));
+    pos += k1 - k0;
+    const int box = col / tiles, tile = col - box * tiles;
+    const int i0 = (tile % tiles_i) * TI, j0 = (tile / tiles_i) * TJ;
+    const int g = L.ghosts;                                          /* tensor coordinates count from the padded origin */
+    const int cx = box * L.nvec + A.x_id, cbi = box * L.nvec + VECTOR_BETA_I, cbj = box * L.nvec + VECTOR_BETA_J, cbk = box * L.nvec + VECTOR_BETA_K;
+    const int ci = i0 - 2 + g, cjx = j0 - 2 + g, cjb = j0 - 1 + g;
+
+    /* prologue: x planes k0-2..k0+2 -> slots 0..4, beta_i/j planes k0-1..k0+1 -> slots 0..2, beta_k k0,k0+1 -> 0,1 */
+    if (tid == 0) {
+      mbar_expect_tx(bar, 5 * C::XBYTES + 8 * C::BBYTES);
+#pragma unroll
+      for (int d = 0; d < 5; d++) tma_load_4d(xs + d * C::XPB, &map_x, ci, cjx, k0 - 2 + d + g, cx, bar);
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        tma_load_4d(bis + d * C::BPB, &map_b, ci, cjb, k0 - 1 + d + g, cbi, bar);
+        tma_load_4d(bjs + d * C::BPB, &map_b, ci, cjb, k0 - 1 + d + g, cbj, bar);
+      }
+#pragma unroll
+      for (int d = 0; d < 2; d++) tma_load_4d(bks + d * C::BPB, &map_b, ci, cjb, k0 + d + g, cbk, bar);
+    }
+
+    const int j = j0 + r;
+    const int cell = (i0 + 2 * p) + j * jS;                        /* pair (2p, 2p+1) of row j, plane 0 */
+    const double *g_rhs = (OP == OP_APPLY) ? nullptr : L.vec(box, A.rhs_id) + cell;
+    const double *g_dinv = (OP == OP_GSRB || OP == OP_CHEBY) ? L.vec(box, VECTOR_DINV) + cell : nullptr;
+    const double *g_xm1 = (OP == OP_CHEBY) ? L.vec(box, A.xm1_id) + cell : nullptr;
+    double *g_out = L.vec(box, A.out_id) + cell;
+    /* which cell of the pair is updated on plane k0 of this sweep (gsrb.c:55,100); flips every plane.
+     * For the uncoloured operators it only fixes the ORDER in which the lane evaluates its two cells
+     * (odd lanes start with the odd cell, so that a half-warp still covers all banks). */
+    int s = (OP == OP_GSRB) ? ((j ^ k0 ^ A.low[3 * box] ^ A.low[3 * box + 1] ^ A.low[3 * box + 2] ^ A.sweep) & 1) : (lane & 1);
+
+    /* point-wise operands (rhs, Dinv, x_{n-1}) are read one plane ahead into registers */
+    double2 rhs_n = make_double2(0.0, 0.0), dinv_n = make_double2(0.0, 0.0), xm_n = make_double2(0.0, 0.0);
+    if (OP != OP_APPLY) rhs_n = *reinterpret_cast<const double2 *>(g_rhs + k0 * kS);
+    if (OP == OP_GSRB || OP == OP_CHEBY) dinv_n = *reinterpret_cast<const double2 *>(g_dinv + k0 * kS);
+    if (OP == OP_CHEBY) xm_n = *reinterpret_cast<const double2 *>(g_xm1 + k0 * kS);
+
+    mbar_wait(bar, phase);
+    phase ^= 1;
+
+    int sx = 0, sb = 0, sk = 0;                                    /* ring slot of planes k-2 (x), k-1 (beta_i/j), k (beta_k) */
+    for (int k = k0; k < k1; k++) {
+      const bool more = (k + 1 < k1);
+      /* ---- the next step's planes go into the spare slots (freed by the barrier that ended step k-1) ---- */
+      if (tid == 0 && more) {
+        const int nx = sx + 5 >= C::XP ? sx + 5 - C::XP : sx + 5;
+        const int nb = sb + 3 >= C::BP ? sb + 3 - C::BP : sb + 3;
+        const int nk = sk + 2 >= C::KP ? sk + 2 - C::KP : sk + 2;
+        mbar_expect_tx(bar, C::XBYTES + 3 * C::BBYTES);
+        tma_load_4d(xs + nx * C::XPB, &map_x, ci, cjx, k + 3 + g, cx, bar);
+        tma_load_4d(bis + nb * C::BPB, &map_b, ci, cjb, k + 2 + g, cbi, bar);
+        tma_load_4d(bjs + nb * C::BPB, &map_b, ci, cjb, k + 2 + g, cbj, bar);
+        tma_load_4d(bks + nk * C::BPB, &map_b, ci, cjb, k + 2 + g, cbk, bar);
+      }
+      const double2 rhs2 = rhs_n, dinv2 = dinv_n, xm2 = xm_n;
+      if (more) {
+        if (OP != OP_APPLY) rhs_n = *reinterpret_cast<const double2 *>(g_rhs + (k + 1) * kS);
+        if (OP == OP_GSRB || OP == OP_CHEBY) dinv_n = *reinterpret_cast<const double2 *>(g_dinv + (k + 1) * kS);
+        if (OP == OP_CHEBY) xm_n = *reinterpret_cast<const double2 *>(g_xm1 + (k + 1) * kS);
+      }
+
+      /* ---- slot addresses of this step's planes ---- */
+      unsigned ax[5], abi[3], abj[3], abk[2];
+#pragma unroll
+      for (int d = 0; d < 5; d++) { const int q = sx + d; ax[d] = xs + (unsigned)((q >= C::XP ? q - C::XP : q) * C::XPB) + lane_x; }
+#pragma unroll
+      for (int d = 0; d < 3; d++) { const int q = sb + d; const unsigned o = (unsigned)((q >= C::BP ? q - C::BP : q) * C::BPB) + lane_b; abi[d] = bis + o; abj[d] = bjs + o; }
+#pragma unroll
+      for (int d = 0; d < 2; d++) { const int q = sk + d; abk[d] = bks + (unsigned)((q >= C::KP ? q - C::KP : q) * C::BPB) + lane_b; }
+
+      SlotLoader<C::W, -2, 5> X;
+      SlotLoader<C::W, -1, 3> BI, BJ;
+      SlotLoader<C::W, 0, 2> BK;
+      double2 out2;
+      if (OP == OP_GSRB) {
+        const unsigned so = (unsigned)(8 * s);
+#pragma unroll
+        for (int d = 0; d < 5; d++) X.a[d] = ax[d] + so;
+#pragma unroll
+        for (int d = 0; d < 3; d++) { BI.a[d] = abi[d] + so; BJ.a[d] = abj[d] + so; }
+#pragma unroll
+        for (int d = 0; d < 2; d++) BK.a[d] = abk[d] + so;
+        const double Ax = fv4_apply_op_at(X, BI, BJ, BK, A.b, A.h2inv);
+        const double xc = X(0, 0, 0);
+        const double xo = lds_f64(ax[2] + (unsigned)(8 * (1 - s)));    /* the pair's other cell: copied (gsrb.c:65-71) */
+        const double xnew = xc + (s ? dinv2.y : dinv2.x) * ((s ? rhs2.y : rhs2.x) - Ax);
+        out2 = s ? make_double2(xo, xnew) : make_double2(xnew, xo);
+        s ^= 1;
+      } else {
+        double res[2];
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+          const int c = s ^ t;                                       /* cell of the pair evaluated in round t */
+          const unsigned so = (unsigned)(8 * c);
+#pragma unroll
+          for (int d = 0; d < 5; d++) X.a[d] = ax[d] + so;
+#pragma unroll
+          for (int d = 0; d < 3; d++) { BI.a[d] = abi[d] + so; BJ.a[d] = abj[d] + so; }
+#pragma unroll
+          for (int d = 0; d < 2; d++) BK.a[d] = abk[d] + so;
+          const double Ax = fv4_apply_op_at(X, BI, BJ, BK, A.b, A.h2inv);
+          double v;
+          if (OP == OP_APPLY) v = Ax;
+          else if (OP == OP_RESIDUAL) v = (c ? rhs2.y : rhs2.x) - Ax;
+          else {                                                     /* OP_CHEBY, chebyshev.c:90 */
+            const double xn = X(0, 0, 0);
+            v = xn + A.c1 * (xn - (c ? xm2.y : xm2.x)) + A.c2 * (c ? dinv2.y : dinv2.x) * ((c ? rhs2.y : rhs2.x) - Ax);
+          }
+          res[t] = v;
+        }
+        out2 = s ? make_double2(res[1], res[0]) : make_double2(res[0], res[1]);
+      }
+      *reinterpret_cast<double2 *>(g_out + k * kS) = out2;
+
+      sx = sx + 1 == C::XP ? 0 : sx + 1;
+      sb = sb + 1 == C::BP ? 0 : sb + 1;
+      sk = sk + 1 == C::KP ? 0 : sk + 1;
+      if (more) { mbar_wait(bar, phase); phase ^= 1; }               /* next step's planes have landed */
+      __syncthreads();                                               /* everyone is done with the oldest slots */
+    }
+  }
+}
+
+#endif

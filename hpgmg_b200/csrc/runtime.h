@@ -27,6 +27,7 @@ int  hpgmg_rt_verbose(void);          /* print reference-style progress lines?  
 int  hpgmg_rt_smoother(void);
 int  hpgmg_rt_use_graphs(void);
 int  hpgmg_rt_profile(void);
+int  hpgmg_rt_sm_count(void);         /* multiprocessors of the current device            */
 int  hpgmg_rt_layout_only(void);   /* host data model only: no device, kernels refuse to launch */
 double hpgmg_rt_wtime(void);          /* host wall clock, seconds                         */
 
