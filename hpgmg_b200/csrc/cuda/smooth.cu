@@ -22,6 +22,7 @@ struct StencilArgs {
   double a, b, h2inv;
   double c1, c2;           /* Chebyshev */
   int sweep;               /* GSRB sweep number s (colour) */
+  int reverse;             /* march k downwards (TMA kernel only; same result) */
 };
 
 /* generic one-thread-per-cell kernel (any box size) ------------------------------------------- */
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(const StencilArgs 
 #include "stencil_tma.cuh"
 #include <vector>
 
-static int g_tiled_async = 1, g_tma = 1, g_tma_blocks = 0, g_tma32 = 0;
+static int g_tiled_async = 1, g_tma = 1, g_tma_blocks = 0, g_tma32 = 1, g_zigzag = 1, g_tma_chunks = 0, g_tma_cfg = 2;
 static int g_force_generic = -1, g_kchunk_override = -1, g_tile32 = 0, g_min_chunk = 16, g_persistent_smooth = 0, g_pair_kernel = 1;
 
 static void stencil_env(void)
@@ -103,6 +104,12 @@ static void stencil_env(void)
     if (tm) g_tma = atoi(tm);
     const char *tb = getenv("HPGMG_B200_TMA_BLOCKS");
     if (tb) g_tma_blocks = atoi(tb);
+    const char *zz = getenv("HPGMG_B200_ZIGZAG");
+    if (zz) g_zigzag = atoi(zz);
+    const char *tc = getenv("HPGMG_B200_TMA_CHUNKS");
+    if (tc) g_tma_chunks = atoi(tc);
+    const char *cf = getenv("HPGMG_B200_TMA_CFG");
+    if (cf) g_tma_cfg = atoi(cf);
     const char *t3 = getenv("HPGMG_B200_TMA32");
     if (t3) g_tma32 = atoi(t3);
     const char *kc = getenv("HPGMG_B200_KCHUNK");
@@ -178,13 +185,14 @@ static const TileMaps *tile_maps(const DLevel &L, const int w, const int xr, con
   return M;
 }
 
-template <int OP, int TI, int TJ>
+template <int OP, int TI, int TJ, int PF, int MINB>
 static void launch_tma(const StencilArgs &A)
 {
-  typedef TmaCfg<TI, TJ> C;
+  typedef TmaCfg<TI, TJ, PF> C;
   static bool configured = false;
   if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(stencil_tma_kernel<OP, TI, TJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    CUDA_CHECK(cudaFuncSetAttribute(stencil_tma_kernel<OP, TI, TJ, PF, MINB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    if (OP == OP_GSRB) CUDA_CHECK(cudaFuncSetAttribute(stencil_tma_kernel<OP, TI, TJ, PF, MINB, (OP == OP_GSRB)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     configured = true;
   }
   const TileMaps *M = tile_maps(A.L, C::W, C::XR, C::BR);
@@ -194,14 +202,31 @@ static void launch_tma(const StencilArgs &A)
    * tiles that are neighbours in j then fetch their common halo rows at the same time and the second
    * fetch hits L2 (measured on `7 8`: 256 blocks = one column each 189 us; 296 blocks with an even but
    * unaligned split of the plane space 234 us).  Chunks only while the grid still fits the resident
-   * slots (2 blocks per SM) and keeps >= 8 planes per block. */
-  const long long slots = 2LL * hpgmg_rt_sm_count(), columns = total / n;
+   * slots (MINB blocks per SM) and keeps >= 8 planes per block. */
+  const long long slots = (long long)MINB * hpgmg_rt_sm_count(), columns = total / n;
   long long chunks = slots / columns;
   if (chunks > n / 8) chunks = n / 8;
   if (chunks < 1) chunks = 1;
+  if (g_tma_chunks > 0) chunks = g_tma_chunks;
   while (n % chunks) chunks--;
   long long blocks = g_tma_blocks > 0 ? g_tma_blocks : columns * chunks;
-  LAUNCH((stencil_tma_kernel<OP, TI, TJ>), dim3((unsigned)blocks), dim3(C::NT), C::SMEM, A, M->x, M->b, total);
+  if (A.reverse && OP == OP_GSRB) LAUNCH((stencil_tma_kernel<OP, TI, TJ, PF, MINB, (OP == OP_GSRB)>), dim3((unsigned)blocks), dim3(C::NT), C::SMEM, A, M->x, M->b, total);
+  else                            LAUNCH((stencil_tma_kernel<OP, TI, TJ, PF, MINB, false>), dim3((unsigned)blocks), dim3(C::NT), C::SMEM, A, M->x, M->b, total);
+}
+
+/* tile shape / prefetch depth / residency of the TMA kernel (HPGMG_B200_TMA_CFG, for experiments) */
+template <int OP>
+static bool launch_tma_cfg(const StencilArgs &A, const int cfg)
+{
+  const int n = A.L.dim;
+  switch (cfg) {
+    case 0: if (n % 64) return false; launch_tma<OP, 64, 8, 1, 2>(A); return true;
+    case 1: if (n % 64) return false; launch_tma<OP, 64, 16, 2, 1>(A); return true;
+    case 2: if (n % 32) return false; launch_tma<OP, 32, 8, 1, 4>(A); return true;
+    case 3: if (n % 32) return false; launch_tma<OP, 32, 16, 2, 2>(A); return true;
+    case 4: if (n % 32) return false; launch_tma<OP, 32, 8, 2, 3>(A); return true;
+    default: return false;
+  }
 }
 
 /* Small even boxes (<= 32^3): one thread per i-PAIR of cells, straight from global memory through L1.
@@ -260,8 +285,8 @@ static void launch_stencil(level_type *level, StencilArgs &A)
   stencil_env();
   if (OP != OP_REBUILD && !g_force_generic) {
     if (n % 32 == 0 && n >= 64 && (g_tile32 == 2 || (g_tile32 == 1 && n == 64))) { launch_tiled<OP, 32, 8>(A); return; }
-    if (n % 64 == 0 && g_tma) { launch_tma<OP, 64, 8>(A); return; }
-    if (n == 32 && g_tma32) { launch_tma<OP, 32, 8>(A); return; }
+    if (n >= 64 && g_tma && launch_tma_cfg<OP>(A, g_tma_cfg)) return;
+    if (n == 32 && g_tma32 && launch_tma_cfg<OP>(A, 2)) return;
     if (n % 64 == 0) { launch_tiled<OP, 64, 8>(A); return; }
     if ((n & 1) == 0 && n >= 4 && g_pair_kernel) {
       const int hn = n / 2;
@@ -315,6 +340,7 @@ static void smooth_gsrb(level_type *level, int x_id, int rhs_id, double a, doubl
     fill_ghosts(level, src);
     StencilArgs A = {};
     A.x_id = src;  A.rhs_id = rhs_id;  A.out_id = dst;  A.a = a;  A.b = b;  A.sweep = s;
+    A.reverse = g_zigzag ? (s & 1) : 0;
     launch_stencil<OP_GSRB>(level, A);
   }
 }

@@ -28,18 +28,19 @@
 #include <cuda.h>
 #include "stencil.cuh"
 
-template <int TI, int TJ>
+template <int TI, int TJ, int PF>
 struct TmaCfg {
   static constexpr int W = TI + 4;                 /* cells i0-2 .. i0+TI+1 of a row                      */
   static constexpr int XR = TJ + 4;                /* x rows    j0-2 .. j0+TJ+1                           */
   static constexpr int BR = TJ + 2;                /* beta rows j0-1 .. j0+TJ                             */
-  static constexpr int XP = 6, BP = 4, KP = 3;     /* ring depths: 5+1, 3+1, 2+1 planes                   */
+  static constexpr int XP = 5 + PF, BP = 3 + PF, KP = 2 + PF;   /* ring depths: planes in use + PF planes in flight */
+  static constexpr int NB = PF + 1;                /* mbarriers: one per step in flight + the one being waited on */
   static constexpr int NT = (TI / 2) * TJ;         /* threads: one per i-pair of cells                    */
   static constexpr int XBYTES = XR * W * 8, BBYTES = BR * W * 8;          /* bytes one TMA copy delivers  */
   static constexpr int XPB = (XBYTES + 127) / 128 * 128;                  /* slot pitch (TMA wants 128-B aligned destinations) */
   static constexpr int BPB = (BBYTES + 127) / 128 * 128;
   static constexpr int OFF_BI = XP * XPB, OFF_BJ = OFF_BI + BP * BPB, OFF_BK = OFF_BJ + BP * BPB, OFF_BAR = OFF_BK + KP * BPB;
-  static constexpr size_t SMEM = (size_t)OFF_BAR + 16 + 128;             /* + mbarrier + alignment slack */
+  static constexpr size_t SMEM = (size_t)OFF_BAR + 8 * NB + 128;         /* + mbarriers + alignment slack */
 };
 
 /* ---- PTX wrappers ---------------------------------------------------------------------------------- */
@@ -87,18 +88,22 @@ struct SlotLoader {
   }
 };
 
-template <int OP, int TI, int TJ>
-__global__ void __launch_bounds__((TI / 2) * TJ, 2)
+/* PF: how many steps ahead the planes are requested.  MINB: resident blocks per SM the register budget is
+ * sized for.  REV: march k downwards -- alternating the direction from sweep to sweep lets a sweep start
+ * on the planes the previous sweep touched last, which are still in the 126 MB L2. */
+template <int OP, int TI, int TJ, int PF, int MINB, bool REV>
+__global__ void __launch_bounds__((TI / 2) * TJ, MINB)
 stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_b, const long long total_planes)
 {
-  typedef TmaCfg<TI, TJ> C;
+  typedef TmaCfg<TI, TJ, PF> C;
   extern __shared__ unsigned char smem_raw[];
   const unsigned s0 = ((unsigned)__cvta_generic_to_shared(smem_raw) + 127u) & ~127u;
-  const unsigned xs = s0, bis = s0 + C::OFF_BI, bjs = s0 + C::OFF_BJ, bks = s0 + C::OFF_BK, bar = s0 + C::OFF_BAR;
+  const unsigned xs = s0, bis = s0 + C::OFF_BI, bjs = s0 + C::OFF_BJ, bks = s0 + C::OFF_BK, bar0 = s0 + C::OFF_BAR;
 
   const int tid = threadIdx.x;
   if (tid == 0) {
-    mbar_init(bar, 1);
+#pragma unroll
+    for (int q = 0; q < C::NB; q++) mbar_init(bar0 + 8 * q, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -119,7 +124,7 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
   /* my share of the linearised (box, tile, k) space */
   const long long lo = total_planes * (long long)blockIdx.x / (long long)gridDim.x;
   const long long hi = total_planes * (long long)(blockIdx.x + 1) / (long long)gridDim.x;
-  unsigned phase = 0;
+  unsigned phasebits = 0;                                           /* bit q: parity of the next wait on mbarrier q */
 
   for (long long pos = lo; pos < hi;) {
     const int col = (int)(pos / n);
@@ -132,18 +137,32 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
     const int cx = box * L.nvec + A.x_id, cbi = box * L.nvec + VECTOR_BETA_I, cbj = box * L.nvec + VECTOR_BETA_J, cbk = box * L.nvec + VECTOR_BETA_K;
     const int ci = i0 - 2 + g, cjx = j0 - 2 + g, cjb = j0 - 1 + g;
 
-    /* prologue: x planes k0-2..k0+2 -> slots 0..4, beta_i/j planes k0-1..k0+1 -> slots 0..2, beta_k k0,k0+1 -> 0,1 */
+    /* Step q (plane kf + q dir) reads x planes q..q+4, beta_i/j planes q..q+2 and beta_k planes q, q+1, counted
+     * in marching order from the first plane each array needs; plane m of an array lives in ring slot m mod depth.
+     * Prologue: everything step 0 needs on mbarrier 0, then what steps 1..PF-1 need in addition, one mbarrier each. */
+    constexpr int dir = REV ? -1 : 1;
+    const int kf = REV ? k1 - 1 : k0, len = k1 - k0;
     if (tid == 0) {
-      mbar_expect_tx(bar, 5 * C::XBYTES + 8 * C::BBYTES);
+      mbar_expect_tx(bar0, 5 * C::XBYTES + 8 * C::BBYTES);
 #pragma unroll
-      for (int d = 0; d < 5; d++) tma_load_4d(xs + d * C::XPB, &map_x, ci, cjx, k0 - 2 + d + g, cx, bar);
+      for (int d = 0; d < 5; d++) tma_load_4d(xs + d * C::XPB, &map_x, ci, cjx, kf + (d - 2) * dir + g, cx, bar0);
 #pragma unroll
       for (int d = 0; d < 3; d++) {
-        tma_load_4d(bis + d * C::BPB, &map_b, ci, cjb, k0 - 1 + d + g, cbi, bar);
-        tma_load_4d(bjs + d * C::BPB, &map_b, ci, cjb, k0 - 1 + d + g, cbj, bar);
+        tma_load_4d(bis + d * C::BPB, &map_b, ci, cjb, kf + (d - 1) * dir + g, cbi, bar0);
+        tma_load_4d(bjs + d * C::BPB, &map_b, ci, cjb, kf + (d - 1) * dir + g, cbj, bar0);
       }
 #pragma unroll
-      for (int d = 0; d < 2; d++) tma_load_4d(bks + d * C::BPB, &map_b, ci, cjb, k0 + d + g, cbk, bar);
+      for (int d = 0; d < 2; d++) tma_load_4d(bks + d * C::BPB, &map_b, ci, cjb, kf + (REV ? 1 - d : d) + g, cbk, bar0);
+#pragma unroll
+      for (int q = 1; q < PF; q++)
+        if (q < len) {
+          const unsigned bq = bar0 + 8 * (q % C::NB);
+          mbar_expect_tx(bq, C::XBYTES + 3 * C::BBYTES);
+          tma_load_4d(xs + ((q + 4) % C::XP) * C::XPB, &map_x, ci, cjx, kf + (q + 2) * dir + g, cx, bq);
+          tma_load_4d(bis + ((q + 2) % C::BP) * C::BPB, &map_b, ci, cjb, kf + (q + 1) * dir + g, cbi, bq);
+          tma_load_4d(bjs + ((q + 2) % C::BP) * C::BPB, &map_b, ci, cjb, kf + (q + 1) * dir + g, cbj, bq);
+          tma_load_4d(bks + ((q + 1) % C::KP) * C::BPB, &map_b, ci, cjb, kf + (REV ? -q : q + 1) + g, cbk, bq);
+        }
     }
 
     const int j = j0 + r;
@@ -155,46 +174,51 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
     /* which cell of the pair is updated on plane k0 of this sweep (gsrb.c:55,100); flips every plane.
      * For the uncoloured operators it only fixes the ORDER in which the lane evaluates its two cells
      * (odd lanes start with the odd cell, so that a half-warp still covers all banks). */
-    int s = (OP == OP_GSRB) ? ((j ^ k0 ^ A.low[3 * box] ^ A.low[3 * box + 1] ^ A.low[3 * box + 2] ^ A.sweep) & 1) : (lane & 1);
+    int s = (OP == OP_GSRB) ? ((j ^ kf ^ A.low[3 * box] ^ A.low[3 * box + 1] ^ A.low[3 * box + 2] ^ A.sweep) & 1) : (lane & 1);
 
     /* point-wise operands (rhs, Dinv, x_{n-1}) are read one plane ahead into registers */
     double2 rhs_n = make_double2(0.0, 0.0), dinv_n = make_double2(0.0, 0.0), xm_n = make_double2(0.0, 0.0);
-    if (OP != OP_APPLY) rhs_n = *reinterpret_cast<const double2 *>(g_rhs + k0 * kS);
-    if (OP == OP_GSRB || OP == OP_CHEBY) dinv_n = *reinterpret_cast<const double2 *>(g_dinv + k0 * kS);
-    if (OP == OP_CHEBY) xm_n = *reinterpret_cast<const double2 *>(g_xm1 + k0 * kS);
+    if (OP != OP_APPLY) rhs_n = *reinterpret_cast<const double2 *>(g_rhs + kf * kS);
+    if (OP == OP_GSRB || OP == OP_CHEBY) dinv_n = *reinterpret_cast<const double2 *>(g_dinv + kf * kS);
+    if (OP == OP_CHEBY) xm_n = *reinterpret_cast<const double2 *>(g_xm1 + kf * kS);
 
-    mbar_wait(bar, phase);
-    phase ^= 1;
+    mbar_wait(bar0, phasebits & 1u);                               /* step 0's planes */
+    phasebits ^= 1u;
 
-    int sx = 0, sb = 0, sk = 0;                                    /* ring slot of planes k-2 (x), k-1 (beta_i/j), k (beta_k) */
-    for (int k = k0; k < k1; k++) {
-      const bool more = (k + 1 < k1);
-      /* ---- the next step's planes go into the spare slots (freed by the barrier that ended step k-1) ---- */
-      if (tid == 0 && more) {
-        const int nx = sx + 5 >= C::XP ? sx + 5 - C::XP : sx + 5;
-        const int nb = sb + 3 >= C::BP ? sb + 3 - C::BP : sb + 3;
-        const int nk = sk + 2 >= C::KP ? sk + 2 - C::KP : sk + 2;
-        mbar_expect_tx(bar, C::XBYTES + 3 * C::BBYTES);
-        tma_load_4d(xs + nx * C::XPB, &map_x, ci, cjx, k + 3 + g, cx, bar);
-        tma_load_4d(bis + nb * C::BPB, &map_b, ci, cjb, k + 2 + g, cbi, bar);
-        tma_load_4d(bjs + nb * C::BPB, &map_b, ci, cjb, k + 2 + g, cbj, bar);
-        tma_load_4d(bks + nk * C::BPB, &map_b, ci, cjb, k + 2 + g, cbk, bar);
+    int sx = 0, sb = 0, sk = 0, bq = 0;                            /* ring slots of the step's first planes; the step's mbarrier */
+    for (int t = 0; t < len; t++) {
+      const int k = kf + t * dir;
+      const bool more = (t + 1 < len);
+      /* ---- request what step t+PF needs in addition: the slots right behind the step's first planes were last
+       *      read in step t-1 (barrier at its end), and mbarrier (t+PF) mod NB was last waited on at the end of step t-2 ---- */
+      if (tid == 0 && t + PF < len) {
+        const int nx = sx == 0 ? C::XP - 1 : sx - 1;
+        const int nb = sb == 0 ? C::BP - 1 : sb - 1;
+        const int nk = sk == 0 ? C::KP - 1 : sk - 1;
+        const int qn = bq == 0 ? C::NB - 1 : bq - 1;                 /* (t + PF) mod NB == (t - 1) mod NB */
+        const unsigned bn = bar0 + 8 * qn;
+        mbar_expect_tx(bn, C::XBYTES + 3 * C::BBYTES);
+        tma_load_4d(xs + nx * C::XPB, &map_x, ci, cjx, k + (PF + 2) * dir + g, cx, bn);
+        tma_load_4d(bis + nb * C::BPB, &map_b, ci, cjb, k + (PF + 1) * dir + g, cbi, bn);
+        tma_load_4d(bjs + nb * C::BPB, &map_b, ci, cjb, k + (PF + 1) * dir + g, cbj, bn);
+        tma_load_4d(bks + nk * C::BPB, &map_b, ci, cjb, k + (REV ? -PF : PF + 1) + g, cbk, bn);
       }
       const double2 rhs2 = rhs_n, dinv2 = dinv_n, xm2 = xm_n;
       if (more) {
-        if (OP != OP_APPLY) rhs_n = *reinterpret_cast<const double2 *>(g_rhs + (k + 1) * kS);
-        if (OP == OP_GSRB || OP == OP_CHEBY) dinv_n = *reinterpret_cast<const double2 *>(g_dinv + (k + 1) * kS);
-        if (OP == OP_CHEBY) xm_n = *reinterpret_cast<const double2 *>(g_xm1 + (k + 1) * kS);
+        if (OP != OP_APPLY) rhs_n = *reinterpret_cast<const double2 *>(g_rhs + (k + dir) * kS);
+        if (OP == OP_GSRB || OP == OP_CHEBY) dinv_n = *reinterpret_cast<const double2 *>(g_dinv + (k + dir) * kS);
+        if (OP == OP_CHEBY) xm_n = *reinterpret_cast<const double2 *>(g_xm1 + (k + dir) * kS);
       }
 
-      /* ---- slot addresses of this step's planes ---- */
+      /* ---- slot addresses of this step's planes, indexed by plane offset (ring position r holds plane
+       *      k + (r - 2) dir for x, k + (r - 1) dir for beta_i/j, and the step's two beta_k planes in marching order) ---- */
       unsigned ax[5], abi[3], abj[3], abk[2];
 #pragma unroll
-      for (int d = 0; d < 5; d++) { const int q = sx + d; ax[d] = xs + (unsigned)((q >= C::XP ? q - C::XP : q) * C::XPB) + lane_x; }
+      for (int d = 0; d < 5; d++) { const int q = sx + d; ax[REV ? 4 - d : d] = xs + (unsigned)((q >= C::XP ? q - C::XP : q) * C::XPB) + lane_x; }
 #pragma unroll
-      for (int d = 0; d < 3; d++) { const int q = sb + d; const unsigned o = (unsigned)((q >= C::BP ? q - C::BP : q) * C::BPB) + lane_b; abi[d] = bis + o; abj[d] = bjs + o; }
+      for (int d = 0; d < 3; d++) { const int q = sb + d; const unsigned o = (unsigned)((q >= C::BP ? q - C::BP : q) * C::BPB) + lane_b; abi[REV ? 2 - d : d] = bis + o; abj[REV ? 2 - d : d] = bjs + o; }
 #pragma unroll
-      for (int d = 0; d < 2; d++) { const int q = sk + d; abk[d] = bks + (unsigned)((q >= C::KP ? q - C::KP : q) * C::BPB) + lane_b; }
+      for (int d = 0; d < 2; d++) { const int q = sk + d; abk[REV ? 1 - d : d] = bks + (unsigned)((q >= C::KP ? q - C::KP : q) * C::BPB) + lane_b; }
 
       SlotLoader<C::W, -2, 5> X;
       SlotLoader<C::W, -1, 3> BI, BJ;
@@ -243,7 +267,11 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
       sx = sx + 1 == C::XP ? 0 : sx + 1;
       sb = sb + 1 == C::BP ? 0 : sb + 1;
       sk = sk + 1 == C::KP ? 0 : sk + 1;
-      if (more) { mbar_wait(bar, phase); phase ^= 1; }               /* next step's planes have landed */
+      bq = bq + 1 == C::NB ? 0 : bq + 1;
+      if (more) {                                                    /* the next step's planes have landed */
+        mbar_wait(bar0 + 8 * bq, (phasebits >> bq) & 1u);
+        phasebits ^= 1u << bq;
+      }
       __syncthreads();                                               /* everyone is done with the oldest slots */
     }
   }
