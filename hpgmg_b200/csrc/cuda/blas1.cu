@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(256) blas1_kernel(const BlasArgs A)
 template <int OP>
 static void launch_blas1(level_type *level, BlasArgs &A)
 {
+  if (hpgmg_ablate(128)) return;
   const DLevel &L = dl_of(level);
   if (L.nboxes == 0) return;
   A.L = L;

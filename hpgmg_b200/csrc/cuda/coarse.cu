@@ -40,8 +40,15 @@ struct CoarseLevel {
   int slab_doubles;
 };
 
+/* phase clocks of the last profiled launch (hpgmg_b200_coarse_profile): SM cycles per category */
+enum { CP_LOAD = 0, CP_FILL, CP_STENCIL, CP_RESTRICT, CP_ZERO, CP_INTERP, CP_BOTTOM, CP_STORE, CP_TOTAL, CP_N };
+__device__ long long g_coarse_prof[CP_N];
+__shared__ long long s_prof[CP_N + 1];
+#define CPROF(cat) do { if (s_prof_on && threadIdx.x == 0) { const long long t_ = clock64(); s_prof[cat] += t_ - s_prof[CP_N]; s_prof[CP_N] = t_; } } while (0)
+__shared__ int s_prof_on;
+
 struct CoarseArgs {
-  int nlevels, mode, smoother, zero_bottom;
+  int nlevels, mode, smoother, zero_bottom, profile;
   int e_id, R_id;
   double a, b, rtol;
   double *krylov;
@@ -70,6 +77,7 @@ __device__ static void c_fill_ghosts(const CoarseLevel &V, const int id, const b
     }
   }
   __syncthreads();
+  CPROF(CP_FILL);
 }
 
 /* one sweep / residual over every cell of every box.  mode: 0 GSRB sweep s, 1 Chebyshev sweep s, 2 residual.
@@ -107,6 +115,7 @@ __device__ static void c_stencil_pairs(const CoarseLevel &V, const int mode, con
     }
   }
   __syncthreads();
+  CPROF(CP_STENCIL);
 }
 
 /* the same, one thread per cell (odd box sizes) */
@@ -133,10 +142,12 @@ __device__ static void c_stencil(const CoarseLevel &V, const int mode, const int
     else { const double xn = x[0]; out[0] = xn + V.c1[s] * (xn - out[0]) + V.c2[s] * dinv * (rhs - Ax); }
   }
   __syncthreads();
+  CPROF(CP_STENCIL);
 }
 
-__device__ static void c_smooth(const CoarseArgs &A, const CoarseLevel &V, const int x_id, const int rhs_id)
+__device__ __noinline__ static void c_smooth(const CoarseArgs &A, const CoarseLevel &V, const int x_id, const int rhs_id)
 {
+#pragma unroll 1
   for (int s = 0; s < 6; s++) {
     const int src = (s & 1) ? VECTOR_TEMP : x_id, dst = (s & 1) ? x_id : VECTOR_TEMP;
     c_fill_ghosts(V, src, false, false);
@@ -153,6 +164,7 @@ __device__ static void c_zero(const DLevel &L, const int id)
     L.vec(box, id)[i + j * L.jStride + k * L.kStride] = 0.0;
   }
   __syncthreads();
+  CPROF(CP_ZERO);
 }
 
 /* restriction.c:54-57 over the local list of the fine level */
@@ -172,6 +184,7 @@ __device__ static void c_restrict_cell(const DLevel &Lc, const int id_c, const D
     }
   }
   __syncthreads();
+  CPROF(CP_RESTRICT);
 }
 
 __device__ __forceinline__ void c_pro3(const double cm, const double c0, const double cp, double &lo, double &hi)
@@ -233,6 +246,7 @@ __device__ static void c_interpolate(const DLevel &Lf, const int id_f, const dou
     }
   }
   __syncthreads();
+  CPROF(CP_INTERP);
 }
 
 __device__ static void c_bottom_solve(const CoarseArgs &A, double *prod, double *red)
@@ -243,12 +257,14 @@ __device__ static void c_bottom_solve(const CoarseArgs &A, double *prod, double 
   B.x_id = A.e_id;  B.R_id = A.R_id;  B.a = A.a;  B.b = A.b;  B.h2inv = V.h2inv;  B.rtol = A.rtol;  B.iters = A.krylov;
   bicgstab_solve(B, prod, red);
   __syncthreads();
+  CPROF(CP_BOTTOM);
 }
 
 /* MGVCycle(level c) for chain index c (mg.c:1135-1164), written as the two loops of the recursion */
-__device__ static void c_vcycle(const CoarseArgs &A, const int c, double *prod, double *red)
+__device__ __noinline__ static void c_vcycle(const CoarseArgs &A, const int c, double *prod, double *red)
 {
   const int bottom = A.nlevels - 1;
+#pragma unroll 1
   for (int l = c; l < bottom; l++) {
     const CoarseLevel &V = A.lv[l], &Vc = A.lv[l + 1];
     c_smooth(A, V, A.e_id, A.R_id);
@@ -258,6 +274,7 @@ __device__ static void c_vcycle(const CoarseArgs &A, const int c, double *prod, 
     c_zero(Vc.L, A.e_id);
   }
   c_bottom_solve(A, prod, red);
+#pragma unroll 1
   for (int l = bottom - 1; l >= c; l--) {
     const CoarseLevel &V = A.lv[l], &Vc = A.lv[l + 1];
     c_fill_ghosts(Vc, A.e_id, true, true);                        /* interpolation_v2: exchange(BOX) + apply_BCs_v2 on the coarse level */
@@ -279,6 +296,7 @@ __global__ void __launch_bounds__(COARSE_THREADS, 1) coarse_cycle_kernel(const _
   double *prod = dyn + ARGS_DOUBLES;
   double *red = prod + BOTTOM_MAX_CELLS + 1;
   double *pool = red + 34;
+  if (threadIdx.x == 0) { s_prof_on = Ain.profile; for (int c = 0; c < CP_N; c++) s_prof[c] = 0; s_prof[CP_N] = clock64(); s_prof[CP_TOTAL] = -s_prof[CP_N]; }
 
   {                                                                /* stage the arguments, then patch the resident levels */
     const int *src = reinterpret_cast<const int *>(&Ain);
@@ -296,6 +314,7 @@ __global__ void __launch_bounds__(COARSE_THREADS, 1) coarse_cycle_kernel(const _
     if (threadIdx.x == 0) A.lv[l].L.base = copy;
   }
   __syncthreads();
+  CPROF(CP_LOAD);
 
   if (A.mode == MODE_VCYCLE) {
     c_vcycle(A, 0, prod, red);
@@ -303,6 +322,7 @@ __global__ void __launch_bounds__(COARSE_THREADS, 1) coarse_cycle_kernel(const _
     const int bottom = A.nlevels - 1;
     if (A.zero_bottom) c_zero(A.lv[bottom].L, A.e_id);              /* mg.c:1285: only if the bottom is not the solve level */
     c_bottom_solve(A, prod, red);
+#pragma unroll 1
     for (int l = bottom - 1; l >= 0; l--) {
       const CoarseLevel &V = A.lv[l], &Vc = A.lv[l + 1];
       c_fill_ghosts(Vc, A.e_id, true, false);                       /* interpolation_v4: exchange(BOX) + apply_BCs_v4 */
@@ -326,11 +346,24 @@ __global__ void __launch_bounds__(COARSE_THREADS, 1) coarse_cycle_kernel(const _
       for (int q = threadIdx.x; q < per_vec; q += blockDim.x) g2[q] = c2[q];
     }
   }
+  __syncthreads();
+  CPROF(CP_STORE);
+  if (s_prof_on && threadIdx.x == 0) { s_prof[CP_TOTAL] += clock64(); for (int c = 0; c < CP_N; c++) g_coarse_prof[c] = s_prof[c]; }
 }
 
 /* ---- host side ------------------------------------------------------------------------------------ */
 static int g_coarse_enabled = -1;
 static int g_coarse_smem = 1;
+static int g_coarse_profile = 0;
+/* cycles per phase category of the next/last coarse kernel launch: load, fill, stencil, restrict, zero, interp, bottom, store, total */
+extern "C" void hpgmg_b200_coarse_profile(int on, long long *out9)
+{
+  g_coarse_profile = on;
+  if (out9) {
+    CUDA_CHECK(cudaStreamSynchronize(g_stream));
+    CUDA_CHECK(cudaMemcpyFromSymbol(out9, g_coarse_prof, sizeof(long long) * CP_N));
+  }
+}
 /* single-block cycles pay off up to 8^3 (one cell per thread, latency-bound); 16^3 is faster as separate launches */
 static long g_coarse_max_cells = 512;
 extern "C" void hpgmg_b200_coarse_levels_in_smem(int on) { g_coarse_smem = on ? 1 : 0; }
@@ -378,6 +411,7 @@ extern "C" void hpgmg_coarse_cycle(mg_type *MG, int from, int mode_ftail, int ze
   A.mode = mode_ftail ? MODE_FTAIL : MODE_VCYCLE;
   A.smoother = hpgmg_rt_smoother();
   A.zero_bottom = zero_bottom;
+  A.profile = g_coarse_profile;
   A.e_id = e_id;  A.R_id = R_id;  A.a = a;  A.b = b;  A.rtol = MG_DEFAULT_BOTTOM_NORM;
   A.krylov = hpgmg_rt_scalar_slots() + HPGMG_SLOT_KRYLOV;
   for (int l = from; l <= bottom; l++) {
@@ -401,7 +435,7 @@ extern "C" void hpgmg_coarse_cycle(mg_type *MG, int from, int mode_ftail, int ze
   }
   /* residency: from the bottom up while the slabs fit in the 227 KB of one SM */
   const size_t fixed = sizeof(double) * (size_t)(((sizeof(CoarseArgs) + 15) / 16) * 2 + BOTTOM_MAX_CELLS + 1 + 34);
-  const size_t budget = 232448 - fixed;
+  const size_t budget = 232320 - fixed;
   size_t used = 0;
   for (int l = bottom; l >= from; l--) {
     CoarseLevel &V = A.lv[l - from];
@@ -417,8 +451,9 @@ extern "C" void hpgmg_coarse_cycle(mg_type *MG, int from, int mode_ftail, int ze
   const size_t smem = fixed + used * sizeof(double);
   static size_t configured = 0;
   if (smem > configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(coarse_cycle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
-    configured = 232448;
+    CUDA_CHECK(cudaFuncSetAttribute(coarse_cycle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232320));
+    configured = 232320;
   }
+  if (hpgmg_ablate(4)) return;
   LAUNCH(coarse_cycle_kernel, 1, COARSE_THREADS, smem, A);
 }

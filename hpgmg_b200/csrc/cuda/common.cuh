@@ -30,7 +30,17 @@ void hpgmg_cuda_check(cudaError_t e, const char *what, const char *file, int lin
  * previous kernel drains, and every kernel starts with PDL_WAIT() (griddepcontrol.wait), which
  * blocks until the previous kernel's memory operations are complete and visible.  On the hundreds of
  * microsecond-sized kernels of the coarse levels this hides most of the launch gap. */
+#ifndef HPGMG_PDL_EARLY
+#define HPGMG_PDL_EARLY 0   /* measured: 7.00 vs 6.45 ms per `7 8` solve -- waiting grids take slots from the running one */
+#endif
+/* launch_dependents first: the NEXT kernel's blocks may be scheduled as soon as every block of this one has
+ * started; they then sit in their own griddepcontrol.wait until this grid has completed and flushed, so
+ * nothing is ever read early -- only the launch latency of the next kernel is taken off the critical path. */
+#if HPGMG_PDL_EARLY
+#define PDL_WAIT() asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory")
+#else
 #define PDL_WAIT() asm volatile("griddepcontrol.wait;" ::: "memory")
+#endif
 extern int g_use_pdl;
 void hpgmg_refuse_launch(const char *kernel);
 template <typename... KArgs, typename... Args>
@@ -63,6 +73,29 @@ static inline void hpgmg_launch_cooperative(const char *name, void (*kernel)(KAr
   cfg.numAttrs = 1;
   CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
   g_launches++;
+}
+/* the whole grid as ONE thread-block cluster (<= 16 blocks): barrier.cluster is a hardware barrier between
+ * its blocks, with release/acquire semantics for global memory too */
+template <typename... KArgs, typename... Args>
+static inline void hpgmg_launch_cluster(const char *name, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args)
+{
+  if (hpgmg_rt_layout_only()) hpgmg_refuse_launch(name);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;  cfg.blockDim = block;  cfg.dynamicSmemBytes = smem;  cfg.stream = g_stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = grid.x;  attr[0].val.clusterDim.y = 1;  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 2 : 1;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  g_launches++;
+}
+__device__ __forceinline__ void cluster_barrier()
+{
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 #define LAUNCH(kernel, grid, block, smem, ...) hpgmg_launch(#kernel, kernel, dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__)
 
@@ -139,6 +172,16 @@ struct ProfileScope {
     if (total) *total += dt;
   }
 };
+
+/* timing experiments only (HPGMG_B200_ABLATE=bitmask): skip a class of kernels to see what it costs inside the
+ * replayed graph; results are garbage in that mode.  1 ghost fills dim>=64, 2 ghost fills dim<64, 4 coarse kernel,
+ * 8 stencil kernels dim<64, 16 restriction/interpolation, 32 residual dim>=64, 64 smoother sweeps dim>=64, 128 BLAS1/norm */
+static inline int hpgmg_ablate(const int bit)
+{
+  static int mask = -1;
+  if (mask < 0) { const char *e = getenv("HPGMG_B200_ABLATE"); mask = e ? atoi(e) : 0; }
+  return mask & bit;
+}
 
 static inline const DLevel &dl_of(const level_type *level) { return HPGMG_DEV(level)->L; }
 

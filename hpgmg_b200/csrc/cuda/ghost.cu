@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(256) fill_ghosts_kernel(const FillArgs A)
 void hpgmg_fill_ghosts(level_type *level, int id, int shape, int bc_version)
 {
   ProfileScope prof_(&level->timers.ghostZone_total);
+  if (hpgmg_ablate(level->box_dim >= 64 ? 1 : 2)) return;
   hpgmg_device_level *D = HPGMG_DEV(level);
   const FillTable &T = D->fill[shape];
   const bool dirichlet = level->boundary_condition.type == BC_DIRICHLET && bc_version != 0;

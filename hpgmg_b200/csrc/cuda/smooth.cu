@@ -283,6 +283,7 @@ static void launch_stencil(level_type *level, StencilArgs &A)
   A.h2inv = 1.0 / (level->h * level->h);
   const int n = L.dim;
   stencil_env();
+  if (OP != OP_REBUILD && hpgmg_ablate(n < 64 ? 8 : (OP == OP_RESIDUAL ? 32 : 64))) return;
   if (OP != OP_REBUILD && !g_force_generic) {
     if (n % 32 == 0 && n >= 64 && (g_tile32 == 2 || (g_tile32 == 1 && n == 64))) { launch_tiled<OP, 32, 8>(A); return; }
     if (n >= 64 && g_tma && launch_tma_cfg<OP>(A, g_tma_cfg)) return;
@@ -387,6 +388,9 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &ge
   __syncthreads();
 }
 
+/* CLUSTER: the grid is one thread-block cluster and the phases are separated by the hardware cluster barrier
+ * (boxes <= 16^3: a few thousand pairs, 8 or 16 blocks); otherwise a cooperative grid with a software barrier. */
+template <bool CLUSTER>
 __global__ void __launch_bounds__(256, 1) smooth_persistent_kernel(const SmoothArgs A)
 {
   PDL_WAIT();
@@ -398,7 +402,7 @@ __global__ void __launch_bounds__(256, 1) smooth_persistent_kernel(const SmoothA
   for (int s = 0; s < 6; s++) {
     const int src = (s & 1) ? VECTOR_TEMP : A.x_id, dst = (s & 1) ? A.x_id : VECTOR_TEMP;
     for (int t = gtid; t < A.ncopies + A.nbc; t += gthreads) fill_items(L, src, t, A.copies, A.ncopies, A.bc, A.nbc, A.version);
-    grid_barrier(A.barrier, generation);
+    if (CLUSTER) cluster_barrier(); else grid_barrier(A.barrier, generation);
     for (int q = gtid; q < pairs; q += gthreads) {
       const int box = q / pairs_per_box, c = q - box * pairs_per_box;
       const int p = c % hn, j = (c / hn) % n, k = c / (hn * n);
@@ -424,7 +428,7 @@ __global__ void __launch_bounds__(256, 1) smooth_persistent_kernel(const SmoothA
         *out = make_double2(r0, r1);
       }
     }
-    if (s < 5) grid_barrier(A.barrier, generation);
+    if (s < 5) { if (CLUSTER) cluster_barrier(); else grid_barrier(A.barrier, generation); }
   }
 }
 
@@ -436,7 +440,7 @@ static int smooth_persistent(level_type *level, int x_id, int rhs_id, double a, 
   hpgmg_device_level *D = HPGMG_DEV(level);
   const DLevel &L = D->L;
   stencil_env();
-  if (!g_persistent_smooth || L.nboxes == 0 || (L.dim & 1) || L.dim > 32 || L.dim < 4) return 0;
+  if (!g_persistent_smooth || L.nboxes == 0 || (L.dim & 1) || L.dim > (g_persistent_smooth == 1 ? 32 : 16) || L.dim < 4) return 0;
   if (level->boundary_condition.type != BC_DIRICHLET || level->box_ghosts != 2 || D->fill_nvec != level->numVectors) return 0;
   const communicator_type *C = &level->exchange_ghosts[STENCIL_SHAPE_NO_CORNERS];
   if (C->num_sends > 0 || C->num_recvs > 0) return 0;                       /* neighbours on other GPUs: the kernel-per-phase path */
@@ -457,9 +461,18 @@ static int smooth_persistent(level_type *level, int x_id, int rhs_id, double a, 
   A.barrier = g_smooth_barrier;
   const int pairs = (L.dim / 2) * L.dim * L.dim * L.nboxes;
   int blocks = (pairs + 255) / 256;
+  if (g_persistent_smooth >= 2) {                                           /* one cluster, hardware barrier */
+    const int cmax = g_persistent_smooth >= 16 ? 16 : 8;
+    if (blocks > cmax) blocks = cmax;
+    static bool configured = false;
+    if (!configured) { CUDA_CHECK(cudaFuncSetAttribute(smooth_persistent_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); configured = true; }
+    hpgmg_launch_cluster("smooth_persistent_kernel<cluster>", smooth_persistent_kernel<true>, dim3(blocks), dim3(256), 0, A);
+    (void)a;
+    return 1;
+  }
   if (blocks > 148) blocks = 148;                                           /* one block per SM: all co-resident */
   CUDA_CHECK(cudaMemsetAsync(g_smooth_barrier, 0, sizeof(unsigned int), g_stream));
-  hpgmg_launch_cooperative("smooth_persistent_kernel", smooth_persistent_kernel, dim3(blocks), dim3(256), 0, A);
+  hpgmg_launch_cooperative("smooth_persistent_kernel", smooth_persistent_kernel<false>, dim3(blocks), dim3(256), 0, A);
   (void)a;
   return 1;
 }

@@ -86,6 +86,7 @@ static void run_restriction_list(level_type *level_c, int id_c, level_type *leve
 extern "C" void restriction(level_type *level_c, int id_c, level_type *level_f, int id_f, int restrictionType)
 {
   ProfileScope prof_(&level_f->timers.restriction_total);
+  if (hpgmg_ablate(16)) return;
   hpgmg_device_level *Df = HPGMG_DEV(level_f), *Dc = HPGMG_DEV(level_c);
   communicator_type *Cf = &level_f->restriction[restrictionType], *Cc = &level_c->restriction[restrictionType];
   const int remote = (Cf->num_sends > 0) || (Cc->num_recvs > 0);
@@ -278,6 +279,7 @@ template <int W>
 static void interpolation_driver(level_type *level_f, int id_f, double prescale_f, level_type *level_c, int id_c)
 {
   ProfileScope prof_(&level_f->timers.interpolation_total);
+  if (hpgmg_ablate(16)) return;
   hpgmg_device_level *Df = HPGMG_DEV(level_f), *Dc = HPGMG_DEV(level_c);
   communicator_type *Cc = &level_c->interpolation, *Cf = &level_f->interpolation;
   const int remote = (Cc->num_sends > 0) || (Cf->num_recvs > 0);

@@ -52,6 +52,9 @@ void hpgmg_b200_use_coarse_kernel(int on);
 /* 1 (default): inside that kernel the coarsest levels (as many as fit in 227 KB, from the bottom up)
  * are held in shared memory.  0: they stay in global memory (same bits; for A/B timing). */
 void hpgmg_b200_coarse_levels_in_smem(int on);
+/* phase clocks of the coarse kernel: on=1 makes the next launches record SM cycles per category; out9 (may be NULL)
+ * receives those of the last launch: load, ghost fill, stencil, restriction, zero, interpolation, bottom solve, store, total */
+void hpgmg_b200_coarse_profile(int on, long long *out9);
 
 /* 1: each operator synchronises and adds its device time to level->timers.* like the reference's
  * getTime() brackets (e.g. gsrb.c:37,130).  0 (default): timers only hold MGSolve totals. */
