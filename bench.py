@@ -90,7 +90,7 @@ def reference_arm(args):
     boxes = args.boxes_per_rank * world
     r = run_reference(args.log2_box_dim, boxes, args.warmup, args.steps)
     if r is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/ref_bench missing (reference not built)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/ref_bench missing (reference not built)"})
         return
     value = r["dof"] / r["seconds"]
     line = {"impl": "reference", "metric": "fmg_dof_per_s", "value": value, "unit": "DOF/s", "n_gpus": world,
@@ -101,7 +101,7 @@ def reference_arm(args):
                              "sample": f"{args.steps} FMGSolve after {args.warmup} warm-up, whole workload"},
             "e2e": {"value": value, "unit": "DOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "f_cycle_norm": r["norm"]}
-    print(json.dumps(line))
+    emit(line)
 
 
 def ours(args):
@@ -238,14 +238,32 @@ def ours(args):
                 "gpu_launches": int(launches), "wall_ms_per_step": 1e3 * wall / args.steps,
                 "f_cycle_norm": norm_r, "f_cycle_rel": rel,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": sampler.summary()}
-        print(json.dumps(line))
+        emit(line)
     H.close()
     if dist is not None:
         L.hpgmg_b200_comm_finalize()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # libraries (NCCL's version banner, torchrun) may write to fd 1: keep the real stdout for the JSON line only
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

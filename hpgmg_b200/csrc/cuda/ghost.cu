@@ -135,11 +135,34 @@ struct FillArgs {
   int id, version;
   const blockCopy_type *pack, *unpack;
   int npack, nfill_blocks, nunpack, nlate_blocks;
+  int ncopy_blocks;                              /* the first ncopy_blocks fill blocks copy FILL_BATCH x 256 ghost cells each */
   P2PPlan *plan;
   const FillCopy *copies;  int ncopies;
   const FillBC *bc;        int nbc;
   const FillBC *late;      int nlate;
 };
+
+/* fill block fb: copies in batches (records, then sources, then stores: FILL_BATCH independent loads in flight
+ * per thread -- the copies are latency-, not bandwidth-bound), then one BC column per thread */
+#define FILL_BATCH 4
+__device__ __forceinline__ void fill_block(const FillArgs &A, const int fb)
+{
+  const DLevel &L = A.L;
+  if (fb < A.ncopy_blocks) {
+    double *v = L.base + (size_t)A.id * (size_t)L.volume;
+    const int t0 = fb * (256 * FILL_BATCH) + threadIdx.x;
+    FillCopy c[FILL_BATCH];
+    double val[FILL_BATCH];
+#pragma unroll
+    for (int n = 0; n < FILL_BATCH; n++) { const int t = t0 + n * 256; c[n] = (t < A.ncopies) ? A.copies[t] : FillCopy{ -1, -1 }; }
+#pragma unroll
+    for (int n = 0; n < FILL_BATCH; n++) if (c[n].src >= 0) val[n] = v[c[n].src];
+#pragma unroll
+    for (int n = 0; n < FILL_BATCH; n++) if (c[n].src >= 0) v[c[n].dst] = val[n];
+  } else {
+    fill_items(L, A.id, A.ncopies + (fb - A.ncopy_blocks) * 256 + threadIdx.x, A.copies, A.ncopies, A.bc, A.nbc, A.version);
+  }
+}
 
 __global__ void __launch_bounds__(256) fill_ghosts_kernel(const FillArgs A)
 {
@@ -147,7 +170,7 @@ __global__ void __launch_bounds__(256) fill_ghosts_kernel(const FillArgs A)
   const DLevel &L = A.L;
   int b = blockIdx.x;
   if (b >= A.npack && b < A.npack + A.nfill_blocks && A.plan == nullptr) {            /* single-GPU fast path */
-    fill_items(L, A.id, (b - A.npack) * blockDim.x + threadIdx.x, A.copies, A.ncopies, A.bc, A.nbc, A.version);
+    fill_block(A, b - A.npack);
     return;
   }
   P2PPlan *plan = A.plan;
@@ -166,7 +189,7 @@ __global__ void __launch_bounds__(256) fill_ghosts_kernel(const FillArgs A)
       ll_store(slots + w0 + i + j * B.write.jStride + k * B.write.kStride, rd[i + j * L.jStride + k * L.kStride], flag);
     }
   } else if ((b -= A.npack) < A.nfill_blocks) {                                        /* ---- GPU-local copies + BCs ---- */
-    fill_items(L, A.id, b * blockDim.x + threadIdx.x, A.copies, A.ncopies, A.bc, A.nbc, A.version);
+    fill_block(A, b);
   } else if ((b -= A.nfill_blocks) < A.nunpack) {                                      /* ---- unpack ---- */
     const blockCopy_type B = A.unpack[b];
     const int n = B.subtype;
@@ -227,7 +250,10 @@ void hpgmg_fill_ghosts(level_type *level, int id, int shape, int bc_version)
   A.L = D->L;  A.id = id;  A.version = version;
   A.copies = T.copies;  A.ncopies = T.ncopies;
   A.bc = T.bc;          A.nbc = dirichlet ? T.nbc : 0;
-  A.nfill_blocks = (A.ncopies + A.nbc + 255) / 256;
+  if (level->box_dim >= 64 && hpgmg_ablate(256)) A.ncopies = 0;
+  if (level->box_dim >= 64 && hpgmg_ablate(512)) A.nbc = 0;
+  A.ncopy_blocks = (A.ncopies + 256 * FILL_BATCH - 1) / (256 * FILL_BATCH);
+  A.nfill_blocks = A.ncopy_blocks + (A.nbc + 255) / 256;
   if (remote) {
     A.pack = pack;  A.npack = npack;  A.unpack = unpack;  A.nunpack = nunpack;  A.plan = plan;
     A.late = T.late;  A.nlate = dirichlet ? T.nlate : 0;
