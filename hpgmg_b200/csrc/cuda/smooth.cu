@@ -23,6 +23,9 @@ struct StencilArgs {
   double c1, c2;           /* Chebyshev */
   int sweep;               /* GSRB sweep number s (colour) */
   int reverse;             /* march k downwards (TMA kernel only; same result) */
+  int diag;                /* TMA GSRB kernel: form Dinv = 1/Aii in registers from the face coefficients wherever the stencil
+                              stays clear of the boundary-condition ghost cells (the stored Dinv holds exactly that there) */
+  int dom[3];              /* level dimensions in cells */
 };
 
 /* generic one-thread-per-cell kernel (any box size) ------------------------------------------- */
@@ -82,7 +85,7 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(const StencilArgs 
 #include "stencil_tma.cuh"
 #include <vector>
 
-static int g_tiled_async = 1, g_tma = 1, g_tma_blocks = 0, g_tma32 = 1, g_zigzag = 1, g_tma_chunks = 0, g_tma_cfg = 2;
+static int g_tiled_async = 1, g_tma = 1, g_tma_blocks = 0, g_tma32 = 1, g_zigzag = 1, g_tma_chunks = 0, g_tma_cfg = 2, g_diag = 1;
 static int g_force_generic = -1, g_kchunk_override = -1, g_tile32 = 0, g_min_chunk = 16, g_persistent_smooth = 0, g_pair_kernel = 1;
 
 static void stencil_env(void)
@@ -108,6 +111,8 @@ static void stencil_env(void)
     if (zz) g_zigzag = atoi(zz);
     const char *tc = getenv("HPGMG_B200_TMA_CHUNKS");
     if (tc) g_tma_chunks = atoi(tc);
+    const char *dg = getenv("HPGMG_B200_DIAG");
+    if (dg) g_diag = atoi(dg);
     const char *cf = getenv("HPGMG_B200_TMA_CFG");
     if (cf) g_tma_cfg = atoi(cf);
     const char *t3 = getenv("HPGMG_B200_TMA32");
@@ -281,6 +286,11 @@ static void launch_stencil(level_type *level, StencilArgs &A)
   A.L = L;
   A.low = HPGMG_DEV(level)->low;
   A.h2inv = 1.0 / (level->h * level->h);
+  A.dom[0] = level->dim.i;  A.dom[1] = level->dim.j;  A.dom[2] = level->dim.k;
+  /* the identity behind `diag` needs the 4^3-colour black-box diagonal (rebuild_operator, operators.fv4.c:145-173:
+   * no two cells of a colour within one stencil) and Dirichlet ghost cells that only cells within 2 of the
+   * boundary can see */
+  A.diag = (OP == OP_GSRB && g_diag && level->boundary_condition.type == BC_DIRICHLET && level->dim.i >= 8 && level->dim.j >= 8 && level->dim.k >= 8) ? 1 : 0;
   const int n = L.dim;
   stencil_env();
   if (OP != OP_REBUILD && hpgmg_ablate(n < 64 ? 8 : (OP == OP_RESIDUAL ? 32 : 64))) return;

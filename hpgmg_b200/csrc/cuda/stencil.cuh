@@ -21,8 +21,13 @@
 
 #define STENCIL_TWELFTH (0.0833333333333333333)
 
+/* aii (optional): the diagonal entry of A at this cell, i.e. the same expression evaluated on the unit vector
+ * (x_c = 1, every other point 0) -- what rebuild_operator_blackbox (rebuild.c:127-133) accumulates into Aii for a
+ * cell whose stencil does not reach a boundary-condition ghost cell: 15*(0-1)-(0-0) = -15 on each face, every
+ * mixed difference (+-0)*beta = +-0, so Aii = -b*h2inv*(1/12 * SUM_faces beta*(-15)) with the faces added in the
+ * macro's order.  Dinv = 1.0/Aii (rebuild.c:181) can then be formed in registers instead of being read. */
 template <class XL, class BIL, class BJL, class BKL>
-__device__ __forceinline__ double fv4_apply_op_at(const XL &X, const BIL &BI, const BJL &BJ, const BKL &BK, const double b, const double h2inv)
+__device__ __forceinline__ double fv4_apply_op_at(const XL &X, const BIL &BI, const BJL &BJ, const BKL &BK, const double b, const double h2inv, double *aii = nullptr)
 {
   const double xc = X(0, 0, 0);
   const double xw = X(-1, 0, 0), xe = X(1, 0, 0), xww = X(-2, 0, 0), xee = X(2, 0, 0);
@@ -32,13 +37,18 @@ __device__ __forceinline__ double fv4_apply_op_at(const XL &X, const BIL &BI, co
   const double xwu = X(-1, 0, 1), xwd = X(-1, 0, -1), xeu = X(1, 0, 1), xed = X(1, 0, -1);
   const double xsu = X(0, -1, 1), xsd = X(0, -1, -1), xnu = X(0, 1, 1), xnd = X(0, 1, -1);
 
+  const double bi0 = BI(0, 0, 0), bi1 = BI(1, 0, 0), bj0 = BJ(0, 0, 0), bj1 = BJ(0, 1, 0), bk0 = BK(0, 0, 0), bk1 = BK(0, 0, 1);
   const double axial =
-      BI(0, 0, 0) * (15.0 * (xw - xc) - (xww - xe))
-    + BI(1, 0, 0) * (15.0 * (xe - xc) - (xee - xw))
-    + BJ(0, 0, 0) * (15.0 * (xs - xc) - (xss - xn))
-    + BJ(0, 1, 0) * (15.0 * (xn - xc) - (xnn - xs))
-    + BK(0, 0, 0) * (15.0 * (xd - xc) - (xdd - xu))
-    + BK(0, 0, 1) * (15.0 * (xu - xc) - (xuu - xd));
+      bi0 * (15.0 * (xw - xc) - (xww - xe))
+    + bi1 * (15.0 * (xe - xc) - (xee - xw))
+    + bj0 * (15.0 * (xs - xc) - (xss - xn))
+    + bj1 * (15.0 * (xn - xc) - (xnn - xs))
+    + bk0 * (15.0 * (xd - xc) - (xdd - xu))
+    + bk1 * (15.0 * (xu - xc) - (xuu - xd));
+  if (aii) {
+    const double unit = bi0 * (-15.0) + bi1 * (-15.0) + bj0 * (-15.0) + bj1 * (-15.0) + bk0 * (-15.0) + bk1 * (-15.0);
+    *aii = -b * h2inv * (STENCIL_TWELFTH * unit);
+  }
 
   const double mixed =
       (BI(0, 1, 0) - BI(0, -1, 0)) * (xwn - xn - xws + xs)

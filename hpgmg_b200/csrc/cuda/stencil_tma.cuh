@@ -176,10 +176,23 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
      * (odd lanes start with the odd cell, so that a half-warp still covers all banks). */
     int s = (OP == OP_GSRB) ? ((j ^ kf ^ A.low[3 * box] ^ A.low[3 * box + 1] ^ A.low[3 * box + 2] ^ A.sweep) & 1) : (lane & 1);
 
+    /* Dinv from memory only where a cell of the tile is within 2 cells of the domain boundary (its stencil then
+     * reaches boundary-condition ghost cells and the stored diagonal carries their contribution); elsewhere it is
+     * 1/Aii of the face coefficients the stencil loads anyway (stencil.cuh) -- 8 of the sweep's 56 B/cell less */
+    bool tile_inner = false;
+    int gk0 = 0;
+    if (OP == OP_GSRB && A.diag) {
+      const int gi = A.low[3 * box] + i0, gj = A.low[3 * box + 1] + j0;
+      tile_inner = gi >= 2 && gi + TI <= A.dom[0] - 2 && gj >= 2 && gj + TJ <= A.dom[1] - 2;
+      gk0 = A.low[3 * box + 2];
+    }
+    const int gk_hi = A.dom[2] - 3;
+#define PLANE_NEEDS_DINV(kk) (!(OP == OP_GSRB) || !tile_inner || gk0 + (kk) < 2 || gk0 + (kk) > gk_hi)
+
     /* point-wise operands (rhs, Dinv, x_{n-1}) are read one plane ahead into registers */
     double2 rhs_n = make_double2(0.0, 0.0), dinv_n = make_double2(0.0, 0.0), xm_n = make_double2(0.0, 0.0);
     if (OP != OP_APPLY) rhs_n = *reinterpret_cast<const double2 *>(g_rhs + kf * kS);
-    if (OP == OP_GSRB || OP == OP_CHEBY) dinv_n = *reinterpret_cast<const double2 *>(g_dinv + kf * kS);
+    if ((OP == OP_GSRB || OP == OP_CHEBY) && PLANE_NEEDS_DINV(kf)) dinv_n = *reinterpret_cast<const double2 *>(g_dinv + kf * kS);
     if (OP == OP_CHEBY) xm_n = *reinterpret_cast<const double2 *>(g_xm1 + kf * kS);
 
     mbar_wait(bar0, phasebits & 1u);                               /* step 0's planes */
@@ -206,7 +219,7 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
       const double2 rhs2 = rhs_n, dinv2 = dinv_n, xm2 = xm_n;
       if (more) {
         if (OP != OP_APPLY) rhs_n = *reinterpret_cast<const double2 *>(g_rhs + (k + dir) * kS);
-        if (OP == OP_GSRB || OP == OP_CHEBY) dinv_n = *reinterpret_cast<const double2 *>(g_dinv + (k + dir) * kS);
+        if ((OP == OP_GSRB || OP == OP_CHEBY) && PLANE_NEEDS_DINV(k + dir)) dinv_n = *reinterpret_cast<const double2 *>(g_dinv + (k + dir) * kS);
         if (OP == OP_CHEBY) xm_n = *reinterpret_cast<const double2 *>(g_xm1 + (k + dir) * kS);
       }
 
@@ -232,10 +245,12 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
         for (int d = 0; d < 3; d++) { BI.a[d] = abi[d] + so; BJ.a[d] = abj[d] + so; }
 #pragma unroll
         for (int d = 0; d < 2; d++) BK.a[d] = abk[d] + so;
-        const double Ax = fv4_apply_op_at(X, BI, BJ, BK, A.b, A.h2inv);
+        double aii;
+        const double Ax = fv4_apply_op_at(X, BI, BJ, BK, A.b, A.h2inv, &aii);
         const double xc = X(0, 0, 0);
         const double xo = lds_f64(ax[2] + (unsigned)(8 * (1 - s)));    /* the pair's other cell: copied (gsrb.c:65-71) */
-        const double xnew = xc + (s ? dinv2.y : dinv2.x) * ((s ? rhs2.y : rhs2.x) - Ax);
+        const double dinv = PLANE_NEEDS_DINV(k) ? (s ? dinv2.y : dinv2.x) : 1.0 / aii;
+        const double xnew = xc + dinv * ((s ? rhs2.y : rhs2.x) - Ax);
         out2 = s ? make_double2(xo, xnew) : make_double2(xnew, xo);
         s ^= 1;
       } else {
@@ -274,6 +289,7 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
       }
       __syncthreads();                                               /* everyone is done with the oldest slots */
     }
+#undef PLANE_NEEDS_DINV
   }
 }
 

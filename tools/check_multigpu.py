@@ -15,6 +15,8 @@ H = api.Hierarchy(log2, bpr, my_rank=rank, num_ranks=world, use_graphs=graphs)
 err, order, norms = H.richardson()
 boxes = H.boxes_in_i ** 3
 gold = json.load(open(os.path.join(ROOT, "tests", "golden", "goldens.json")))["solves"].get(f"{log2} {boxes} gsrb")
+if gold is None and (log2, boxes) == (7, 64):      # the reference's own `hpgmg-fv 7 64` run (too big for the fixture generator's box)
+    gold = {"norms": [4.151187785543952e-08, 5.144232180231967e-07, 7.454875249779391e-06], "error": 9.221160350049440e-10}
 if rank == 0:
     ok = gold is not None and [n[0] for n in norms] == gold["norms"] and err == gold["error"]
     print(f"world={world} cfg={log2} {bpr}/rank -> {boxes} boxes, levels={H.num_levels} graphs={graphs} p2p={L.hpgmg_b200_p2p_enabled()}")
