@@ -26,6 +26,7 @@ struct StencilArgs {
   int diag;                /* TMA GSRB kernel: form Dinv = 1/Aii in registers from the face coefficients wherever the stencil
                               stays clear of the boundary-condition ghost cells (the stored Dinv holds exactly that there) */
   int dom[3];              /* level dimensions in cells */
+  int l2hint;              /* TMA kernel: keep the face coefficients in L2 (evict_last); 2: and stream x (evict_first) */
 };
 
 /* generic one-thread-per-cell kernel (any box size) ------------------------------------------- */
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(const StencilArgs 
 #include "stencil_tma.cuh"
 #include <vector>
 
-static int g_tiled_async = 1, g_tma = 1, g_tma_blocks = 0, g_tma32 = 1, g_zigzag = 1, g_tma_chunks = 0, g_tma_cfg = 2, g_diag = 1;
+static int g_tiled_async = 1, g_tma = 1, g_tma_blocks = 0, g_tma32 = 1, g_zigzag = 1, g_tma_chunks = 0, g_tma_cfg = 2, g_diag = 1, g_l2hint = 0, g_l2hint_mb = 100, g_persistent_maxdim = 16;
 static int g_force_generic = -1, g_kchunk_override = -1, g_tile32 = 0, g_min_chunk = 16, g_persistent_smooth = 0, g_pair_kernel = 1;
 
 static void stencil_env(void)
@@ -111,6 +112,12 @@ static void stencil_env(void)
     if (zz) g_zigzag = atoi(zz);
     const char *tc = getenv("HPGMG_B200_TMA_CHUNKS");
     if (tc) g_tma_chunks = atoi(tc);
+    const char *pm = getenv("HPGMG_B200_PERSISTENT_MAXDIM");
+    if (pm) g_persistent_maxdim = atoi(pm);
+    const char *lh = getenv("HPGMG_B200_L2HINT");
+    if (lh) g_l2hint = atoi(lh);
+    const char *lm = getenv("HPGMG_B200_L2HINT_MB");
+    if (lm) g_l2hint_mb = atoi(lm);
     const char *dg = getenv("HPGMG_B200_DIAG");
     if (dg) g_diag = atoi(dg);
     const char *cf = getenv("HPGMG_B200_TMA_CFG");
@@ -230,6 +237,8 @@ static bool launch_tma_cfg(const StencilArgs &A, const int cfg)
     case 2: if (n % 32) return false; launch_tma<OP, 32, 8, 1, 4>(A); return true;
     case 3: if (n % 32) return false; launch_tma<OP, 32, 16, 2, 2>(A); return true;
     case 4: if (n % 32) return false; launch_tma<OP, 32, 8, 2, 3>(A); return true;
+    case 5: if (n % 32) return false; launch_tma<OP, 32, 16, 1, 2>(A); return true;
+    case 6: if (n % 64) return false; launch_tma<OP, 64, 16, 1, 1>(A); return true;
     default: return false;
   }
 }
@@ -287,6 +296,10 @@ static void launch_stencil(level_type *level, StencilArgs &A)
   A.low = HPGMG_DEV(level)->low;
   A.h2inv = 1.0 / (level->h * level->h);
   A.dom[0] = level->dim.i;  A.dom[1] = level->dim.j;  A.dom[2] = level->dim.k;
+  {                         /* operator data (3 betas + rhs) of the boxes on this GPU small enough to live in L2 across sweeps? */
+    const double mb = 4.0 * (double)L.nboxes * (double)L.volume * 8.0 / 1e6;
+    A.l2hint = (g_l2hint && mb <= (double)g_l2hint_mb) ? g_l2hint : 0;
+  }
   /* the identity behind `diag` needs the 4^3-colour black-box diagonal (rebuild_operator, operators.fv4.c:145-173:
    * no two cells of a colour within one stencil) and Dirichlet ghost cells that only cells within 2 of the
    * boundary can see */
@@ -450,7 +463,7 @@ static int smooth_persistent(level_type *level, int x_id, int rhs_id, double a, 
   hpgmg_device_level *D = HPGMG_DEV(level);
   const DLevel &L = D->L;
   stencil_env();
-  if (!g_persistent_smooth || L.nboxes == 0 || (L.dim & 1) || L.dim > (g_persistent_smooth == 1 ? 32 : 16) || L.dim < 4) return 0;
+  if (!g_persistent_smooth || L.nboxes == 0 || (L.dim & 1) || L.dim > (g_persistent_smooth == 1 ? 32 : g_persistent_maxdim) || L.dim < 4) return 0;
   if (level->boundary_condition.type != BC_DIRICHLET || level->box_ghosts != 2 || D->fill_nvec != level->numVectors) return 0;
   const communicator_type *C = &level->exchange_ghosts[STENCIL_SHAPE_NO_CORNERS];
   if (C->num_sends > 0 || C->num_recvs > 0) return 0;                       /* neighbours on other GPUs: the kernel-per-phase path */
