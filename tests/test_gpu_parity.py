@@ -359,3 +359,36 @@ def test_multi_gpu_fmg_equals_single_process_reference(gpu_lib, ranks):
            "--master-port", str(29600 + ranks), os.path.join(root, "tools", "check_multigpu.py"), "5", "8"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "PARITY OK (bit-exact)" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ------------------------------------------------------------------------- kernel variants behind switches
+VARIANTS = [
+    {"HPGMG_B200_TMA_CFG": "0"},                                  # 64x8 tiles, 2 blocks/SM
+    {"HPGMG_B200_TMA_CFG": "1"},                                  # 64x16 tiles, planes requested two steps ahead
+    {"HPGMG_B200_TMA_CFG": "3"},                                  # 32x16, two steps ahead
+    {"HPGMG_B200_TMA_CFG": "4"},                                  # 32x8, two steps ahead
+    {"HPGMG_B200_TMA_CFG": "5"}, {"HPGMG_B200_TMA_CFG": "6"},
+    {"HPGMG_B200_TMA_BLOCKS": "37"},                              # uneven split: blocks own several partial columns
+    {"HPGMG_B200_TMA_BLOCKS": "301", "HPGMG_B200_ZIGZAG": "0"},
+    {"HPGMG_B200_DIAG": "0"},                                     # Dinv always from memory
+    {"HPGMG_B200_L2HINT": "2"},                                   # L2 eviction hints on the TMA loads
+    {"HPGMG_B200_TMA": "0"},                                      # the cp.async kernel
+    {"HPGMG_B200_TMA": "0", "HPGMG_B200_TILED_ASYNC": "0"},       # ... with register staging
+    {"HPGMG_B200_GENERIC_STENCIL": "1"},                          # one thread per cell
+    {"HPGMG_B200_PERSISTENT_SMOOTH": "8"},                        # small levels: one smooth = one cluster kernel
+    {"HPGMG_B200_PERSISTENT_SMOOTH": "1"},                        # ... cooperative grid barrier
+    {"HPGMG_B200_NO_COARSE_KERNEL": "1"},
+]
+
+
+@pytest.mark.parametrize("env", VARIANTS, ids=lambda e: ",".join(f"{k[11:]}={v}" for k, v in e.items()))
+def test_kernel_variants_give_the_same_bits(gpu_lib, env):
+    """Every alternative kernel / schedule kept in the tree behind an environment switch
+    must reproduce the reference goldens of `hpgmg-fv 6 8` (64^3 and 32^3 boxes: the TMA kernel on two levels)."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    e = dict(os.environ)
+    e.update(env)
+    e.pop("RANK", None); e.pop("WORLD_SIZE", None)
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_multigpu.py"), "6", "8"], capture_output=True, text=True, timeout=300, env=e)
+    assert "PARITY OK (bit-exact)" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
