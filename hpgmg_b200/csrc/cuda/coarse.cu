@@ -47,12 +47,21 @@ __shared__ long long s_prof[CP_N + 1];
 #define CPROF(cat) do { if (s_prof_on && threadIdx.x == 0) { const long long t_ = clock64(); s_prof[cat] += t_ - s_prof[CP_N]; s_prof[CP_N] = t_; } } while (0)
 __shared__ int s_prof_on;
 
+/* The cycle is handed to the kernel as a PROGRAM of phases (built on the host by the same recursion the stream
+ * version runs, p_vcycle / p_ftail below) and executed by one loop with one switch, so that every operator body
+ * exists once in the binary: written as nested inlined calls the kernel was 29 k SASS instructions of mostly
+ * straight-line code and its 16 warps spent a third of their issue slots waiting for instruction fetches. */
+enum { PH_FILL = 0, PH_STENCIL, PH_RESTRICT, PH_ZERO, PH_INTERP3, PH_INTERP5, PH_BOTTOM };
+struct Phase { unsigned char op, lv, a, b, c, d, e, pad; };
+#define COARSE_MAX_PHASES 384
+
 struct CoarseArgs {
-  int nlevels, mode, smoother, zero_bottom, profile;
+  int nlevels, mode, smoother, zero_bottom, profile, nphases;
   int e_id, R_id;
   double a, b, rtol;
   double *krylov;
   CoarseLevel lv[COARSE_MAX_LEVELS];
+  Phase prog[COARSE_MAX_PHASES];
 };
 
 /* ---- cooperative (whole thread block) versions of the level operators ---------------------------- */
@@ -87,9 +96,26 @@ __device__ static void c_stencil_pairs(const CoarseLevel &V, const int mode, con
   const DLevel &L = V.L;
   const int n = L.dim, jS = L.jStride, kS = L.kStride;
   const int hn = n >> 1, per_box = hn * n * n, total = per_box * L.nboxes;
+  const bool pow2 = (n & (n - 1)) == 0;                            /* 8, 4, 2: shifts instead of five ~80-cycle integer divisions */
+  const int lg = 31 - __clz(n);
   for (int q = threadIdx.x; q < total; q += blockDim.x) {
-    const int box = q / per_box, c = q - box * per_box;
-    const int p = c % hn, j = (c / hn) % n, k = c / (hn * n);
+    int box, p, j, k;
+    if (pow2) {
+      box = q >> (3 * lg - 1);
+      const int c = q & (per_box - 1);
+      if (n == 8) {
+        /* a warp = 4 pairs x 4 rows x 2 planes: with jStride 12 and kStride 144 the 16 lanes of a plane fall into
+         * 16 distinct 8-byte banks and the two planes (opposite colour) into the same 16 again -- 2 wavefronts per
+         * 64-bit load, the minimum; 4 pairs x 8 rows of one plane would be 4 (rows j and j+4 share banks) */
+        p = c & 3;  j = ((c >> 2) & 3) | (((c >> 5) & 1) << 2);  k = ((c >> 4) & 1) | (((c >> 6) & 3) << 1);
+      } else {
+        p = c & (hn - 1);  j = (c >> (lg - 1)) & (n - 1);  k = c >> (2 * lg - 1);
+      }
+    } else {
+      box = q / per_box;
+      const int c = q - box * per_box;
+      p = c % hn;  j = (c / hn) % n;  k = c / (hn * n);
+    }
     const int ijk = 2 * p + j * jS + k * kS;
     const double *x = L.vec(box, src) + ijk;
     const double *bi = L.vec(box, VECTOR_BETA_I) + ijk, *bj = L.vec(box, VECTOR_BETA_J) + ijk, *bk = L.vec(box, VECTOR_BETA_K) + ijk;
@@ -143,16 +169,6 @@ __device__ static void c_stencil(const CoarseLevel &V, const int mode, const int
   }
   __syncthreads();
   CPROF(CP_STENCIL);
-}
-
-__device__ __noinline__ static void c_smooth(const CoarseArgs &A, const CoarseLevel &V, const int x_id, const int rhs_id)
-{
-#pragma unroll 1
-  for (int s = 0; s < 6; s++) {
-    const int src = (s & 1) ? VECTOR_TEMP : x_id, dst = (s & 1) ? x_id : VECTOR_TEMP;
-    c_fill_ghosts(V, src, false, false);
-    c_stencil(V, A.smoother == HPGMG_SMOOTHER_CHEBY ? 1 : 0, src, dst, rhs_id, s, A.b);
-  }
 }
 
 __device__ static void c_zero(const DLevel &L, const int id)
@@ -260,29 +276,6 @@ __device__ static void c_bottom_solve(const CoarseArgs &A, double *prod, double 
   CPROF(CP_BOTTOM);
 }
 
-/* MGVCycle(level c) for chain index c (mg.c:1135-1164), written as the two loops of the recursion */
-__device__ __noinline__ static void c_vcycle(const CoarseArgs &A, const int c, double *prod, double *red)
-{
-  const int bottom = A.nlevels - 1;
-#pragma unroll 1
-  for (int l = c; l < bottom; l++) {
-    const CoarseLevel &V = A.lv[l], &Vc = A.lv[l + 1];
-    c_smooth(A, V, A.e_id, A.R_id);
-    c_fill_ghosts(V, A.e_id, false, false);                       /* residual(): exchange + BC on x */
-    c_stencil(V, 2, A.e_id, VECTOR_TEMP, A.R_id, 0, A.b);
-    c_restrict_cell(Vc.L, A.R_id, V.L, VECTOR_TEMP, V.restr, V.n_restr);
-    c_zero(Vc.L, A.e_id);
-  }
-  c_bottom_solve(A, prod, red);
-#pragma unroll 1
-  for (int l = bottom - 1; l >= c; l--) {
-    const CoarseLevel &V = A.lv[l], &Vc = A.lv[l + 1];
-    c_fill_ghosts(Vc, A.e_id, true, true);                        /* interpolation_v2: exchange(BOX) + apply_BCs_v2 on the coarse level */
-    c_interpolate<3>(V.L, A.e_id, 1.0, Vc.L, A.e_id, Vc.interp, Vc.n_interp);
-    c_smooth(A, V, A.e_id, A.R_id);
-  }
-}
-
 /* The coarsest levels (8^3, 4^3, 2^3 in the benchmark: 200 KB with all their vectors) are copied into
  * shared memory for the duration of the kernel: DLevel::base is simply pointed at the copy, so every
  * operator body works on it unchanged, at shared-memory instead of L2 latency.  Everything except the
@@ -316,18 +309,18 @@ __global__ void __launch_bounds__(COARSE_THREADS, 1) coarse_cycle_kernel(const _
   __syncthreads();
   CPROF(CP_LOAD);
 
-  if (A.mode == MODE_VCYCLE) {
-    c_vcycle(A, 0, prod, red);
-  } else {                                                          /* MODE_FTAIL: mg.c:1285-1301 restricted to the chain */
-    const int bottom = A.nlevels - 1;
-    if (A.zero_bottom) c_zero(A.lv[bottom].L, A.e_id);              /* mg.c:1285: only if the bottom is not the solve level */
-    c_bottom_solve(A, prod, red);
 #pragma unroll 1
-    for (int l = bottom - 1; l >= 0; l--) {
-      const CoarseLevel &V = A.lv[l], &Vc = A.lv[l + 1];
-      c_fill_ghosts(Vc, A.e_id, true, false);                       /* interpolation_v4: exchange(BOX) + apply_BCs_v4 */
-      c_interpolate<5>(V.L, A.e_id, 0.0, Vc.L, A.e_id, Vc.interp, Vc.n_interp);
-      c_vcycle(A, l, prod, red);
+  for (int ph = 0; ph < A.nphases; ph++) {
+    const Phase P = A.prog[ph];
+    const CoarseLevel &V = A.lv[P.lv];
+    switch (P.op) {
+      case PH_FILL:     c_fill_ghosts(V, P.a, P.b != 0, P.c != 0); break;
+      case PH_STENCIL:  c_stencil(V, P.a, P.b, P.c, P.d, P.e, A.b); break;
+      case PH_RESTRICT: c_restrict_cell(A.lv[P.lv + 1].L, P.a, V.L, P.b, V.restr, V.n_restr); break;
+      case PH_ZERO:     c_zero(V.L, P.a); break;
+      case PH_INTERP3:  c_interpolate<3>(V.L, P.a, 1.0, A.lv[P.lv + 1].L, P.b, A.lv[P.lv + 1].interp, A.lv[P.lv + 1].n_interp); break;
+      case PH_INTERP5:  c_interpolate<5>(V.L, P.a, 0.0, A.lv[P.lv + 1].L, P.b, A.lv[P.lv + 1].interp, A.lv[P.lv + 1].n_interp); break;
+      default:          c_bottom_solve(A, prod, red); break;
     }
   }
 
@@ -352,6 +345,7 @@ __global__ void __launch_bounds__(COARSE_THREADS, 1) coarse_cycle_kernel(const _
 }
 
 /* ---- host side ------------------------------------------------------------------------------------ */
+static int coarse_program_length(int nlevels, int ftail);
 static int g_coarse_enabled = -1;
 static int g_coarse_smem = 1;
 static int g_coarse_profile = 0;
@@ -396,11 +390,57 @@ extern "C" int hpgmg_coarse_chain_eligible(mg_type *MG, int from)
   if (!g_coarse_enabled) return 0;
   const int bottom = MG->num_levels - 1;
   if (from > bottom || bottom - from + 1 > COARSE_MAX_LEVELS) return 0;
+  if (coarse_program_length(bottom - from + 1, 1) > COARSE_MAX_PHASES) return 0;
   for (int l = from; l <= bottom; l++) if (!level_is_coarse_eligible(MG->levels[l], l == from, l == bottom)) return 0;
   const level_type *B = MG->levels[bottom];
   if (B->num_my_boxes != 1 || B->boxes_in.i != 1 || B->box_dim > BOTTOM_MAX_DIM || B->box_dim < 2) return 0;
   if (B->numVectors < VECTORS_RESERVED + 8) return 0;
   return 1;
+}
+
+/* ---- the phase program: the recursion of the stream version, recorded instead of executed ---- */
+static void p_add(CoarseArgs &A, int op, int lv, int a = 0, int b = 0, int c = 0, int d = 0, int e = 0)
+{
+  if (A.nphases >= COARSE_MAX_PHASES) { fprintf(stderr, "hpgmg_b200: coarse-cycle program too long\n"); exit(1); }
+  Phase P = { (unsigned char)op, (unsigned char)lv, (unsigned char)a, (unsigned char)b, (unsigned char)c, (unsigned char)d, (unsigned char)e, 0 };
+  A.prog[A.nphases++] = P;
+  static int repeat = -1;                       /* timing experiment: run the idempotent phases twice (warm instruction / data caches?) */
+  if (repeat < 0) { const char *r = getenv("HPGMG_B200_COARSE_REPEAT"); repeat = r ? atoi(r) : 0; }
+  if (repeat && (op == PH_FILL || op == PH_STENCIL) && A.nphases < COARSE_MAX_PHASES) A.prog[A.nphases++] = P;
+}
+static void p_smooth(CoarseArgs &A, int l, int x_id, int rhs_id)            /* smooth(): gsrb.c:24-132 / chebyshev.c:8-100 */
+{
+  for (int s = 0; s < 6; s++) {
+    const int src = (s & 1) ? VECTOR_TEMP : x_id, dst = (s & 1) ? x_id : VECTOR_TEMP;
+    p_add(A, PH_FILL, l, src, 0, 0);
+    p_add(A, PH_STENCIL, l, A.smoother == HPGMG_SMOOTHER_CHEBY ? 1 : 0, src, dst, rhs_id, s);
+  }
+}
+static void p_vcycle(CoarseArgs &A, int c)                                 /* MGVCycle: mg.c:1135-1164 */
+{
+  const int bottom = A.nlevels - 1;
+  for (int l = c; l < bottom; l++) {
+    p_smooth(A, l, A.e_id, A.R_id);
+    p_add(A, PH_FILL, l, A.e_id, 0, 0);                                    /* residual(): exchange + BC on x */
+    p_add(A, PH_STENCIL, l, 2, A.e_id, VECTOR_TEMP, A.R_id, 0);
+    p_add(A, PH_RESTRICT, l, A.R_id, VECTOR_TEMP);
+    p_add(A, PH_ZERO, l + 1, A.e_id);
+  }
+  p_add(A, PH_BOTTOM, bottom);
+  for (int l = bottom - 1; l >= c; l--) {
+    p_add(A, PH_FILL, l + 1, A.e_id, 1, 1);                                /* interpolation_v2: exchange(BOX) + apply_BCs_v2 on the coarse level */
+    p_add(A, PH_INTERP3, l, A.e_id, A.e_id);
+    p_smooth(A, l, A.e_id, A.R_id);
+  }
+}
+static int coarse_program_length(int nlevels, int ftail)
+{
+  int v = 0, total = 0;                                                     /* phases of MGVCycle(c): 30 per non-bottom level + 1 */
+  for (int c = nlevels - 1; c >= 0; c--) {
+    v = 30 * (nlevels - 1 - c) + 1;
+    if (ftail && c < nlevels - 1) total += 2 + v;
+  }
+  return ftail ? total + 2 : v;
 }
 
 extern "C" void hpgmg_coarse_cycle(mg_type *MG, int from, int mode_ftail, int zero_bottom, int e_id, int R_id, double a, double b)
@@ -448,6 +488,18 @@ extern "C" void hpgmg_coarse_cycle(mg_type *MG, int from, int mode_ftail, int ze
     } else break;                                                    /* keep the resident set contiguous from the bottom */
   }
   for (int l = from; l <= bottom; l++) if (A.lv[l - from].smem_offset < 0) { A.lv[l - from].smem_offset = -1; }
+  A.nphases = 0;
+  if (A.mode == MODE_VCYCLE) p_vcycle(A, 0);
+  else {                                                                    /* MODE_FTAIL: mg.c:1285-1301 restricted to the chain */
+    const int cb = A.nlevels - 1;
+    if (A.zero_bottom) p_add(A, PH_ZERO, cb, A.e_id);                       /* mg.c:1285: only if the bottom is not the solve level */
+    p_add(A, PH_BOTTOM, cb);
+    for (int l = cb - 1; l >= 0; l--) {
+      p_add(A, PH_FILL, l + 1, A.e_id, 1, 0);                               /* interpolation_v4: exchange(BOX) + apply_BCs_v4 */
+      p_add(A, PH_INTERP5, l, A.e_id, A.e_id);
+      p_vcycle(A, l);
+    }
+  }
   const size_t smem = fixed + used * sizeof(double);
   static size_t configured = 0;
   if (smem > configured) {

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(const StencilArgs 
 #include "stencil_tma.cuh"
 #include <vector>
 
-static int g_tiled_async = 1, g_tma = 1, g_tma_blocks = 0, g_tma32 = 1, g_zigzag = 1, g_tma_chunks = 0, g_tma_cfg = 2, g_diag = 1, g_l2hint = 0, g_l2hint_mb = 100, g_persistent_maxdim = 16;
+static int g_tiled_async = 1, g_tma = 1, g_tma_blocks = 0, g_tma32 = 1, g_zigzag = 1, g_tma_chunks = 0, g_tma_cfg = 2, g_tma_cfg_full = 2, g_diag = 1, g_l2hint = 0, g_l2hint_mb = 100, g_persistent_maxdim = 16;
 static int g_force_generic = -1, g_kchunk_override = -1, g_tile32 = 0, g_min_chunk = 16, g_persistent_smooth = 0, g_pair_kernel = 1;
 
 static void stencil_env(void)
@@ -121,7 +121,9 @@ static void stencil_env(void)
     const char *dg = getenv("HPGMG_B200_DIAG");
     if (dg) g_diag = atoi(dg);
     const char *cf = getenv("HPGMG_B200_TMA_CFG");
-    if (cf) g_tma_cfg = atoi(cf);
+    if (cf) g_tma_cfg = g_tma_cfg_full = atoi(cf);
+    const char *cr = getenv("HPGMG_B200_TMA_CFG_FULL");      /* the operators that evaluate every cell: residual, Chebyshev, apply_op */
+    if (cr) g_tma_cfg_full = atoi(cr);
     const char *t3 = getenv("HPGMG_B200_TMA32");
     if (t3) g_tma32 = atoi(t3);
     const char *kc = getenv("HPGMG_B200_KCHUNK");
@@ -309,7 +311,7 @@ static void launch_stencil(level_type *level, StencilArgs &A)
   if (OP != OP_REBUILD && hpgmg_ablate(n < 64 ? 8 : (OP == OP_RESIDUAL ? 32 : 64))) return;
   if (OP != OP_REBUILD && !g_force_generic) {
     if (n % 32 == 0 && n >= 64 && (g_tile32 == 2 || (g_tile32 == 1 && n == 64))) { launch_tiled<OP, 32, 8>(A); return; }
-    if (n >= 64 && g_tma && launch_tma_cfg<OP>(A, g_tma_cfg)) return;
+    if (n >= 64 && g_tma && launch_tma_cfg<OP>(A, OP == OP_GSRB ? g_tma_cfg : g_tma_cfg_full)) return;
     if (n == 32 && g_tma32 && launch_tma_cfg<OP>(A, 2)) return;
     if (n % 64 == 0) { launch_tiled<OP, 64, 8>(A); return; }
     if ((n & 1) == 0 && n >= 4 && g_pair_kernel) {
