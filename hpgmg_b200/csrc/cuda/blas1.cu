@@ -148,6 +148,58 @@ __global__ void __launch_bounds__(256) norm_kernel(const DLevel L, const int id,
   }
 }
 
+/* c = 1.0 * a together with max |a| (FMGSolve / MGSolve begin with norm(F); R = F: mg.c:1259-1262): one pass over F */
+__global__ void __launch_bounds__(256) copy_norm_kernel(const DLevel L, const int id_c, const int id_a, double *__restrict__ slot)
+{
+  PDL_WAIT();
+  const int n = L.dim, box = blockIdx.y;
+  const double *__restrict__ v = L.vec(box, id_a);
+  double *__restrict__ c = L.vec(box, id_c);
+  double m = 0.0;
+  const int hn = n / 2, pairs = hn * n * n;                /* even n only: rows start 16-byte aligned */
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < pairs; q += gridDim.x * blockDim.x) {
+    const int p = q % hn, j = (q / hn) % n, k = q / (hn * n);
+    const int ijk = 2 * p + j * L.jStride + k * L.kStride;
+    const double2 a = *reinterpret_cast<const double2 *>(v + ijk);
+    *reinterpret_cast<double2 *>(c + ijk) = make_double2(1.0 * a.x, 1.0 * a.y);
+    const double f0 = fabs(a.x), f1 = fabs(a.y);
+    if (f0 > m) m = f0;
+    if (f1 > m) m = f1;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double other = __shfl_down_sync(0xffffffffu, m, o);
+    if (other > m) m = other;
+  }
+  __shared__ double wmax[8];
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) if (wmax[w] > m) m = wmax[w];
+    atomic_max_nonneg(slot, m);
+  }
+}
+
+extern "C" void hpgmg_norm_async(level_type *level, int id_a, int slot);
+/* norm(level, id_a) into `slot` and scale_vector(level, id_c, 1.0, id_a) */
+extern "C" void hpgmg_copy_norm_async(level_type *level, int id_c, int id_a, int slot)
+{
+  const DLevel &L = dl_of(level);
+  static int fuse = -1;
+  if (fuse < 0) { const char *e = getenv("HPGMG_B200_FUSE_NORM"); fuse = e ? atoi(e) : 1; }
+  if (!fuse || hpgmg_rt_profile() || (L.dim & 1) || hpgmg_ablate(128)) { hpgmg_norm_async(level, id_a, slot); scale_vector(level, id_c, 1.0, id_a); return; }
+  double *s = hpgmg_rt_scalar_slots() + slot;
+  CUDA_CHECK(cudaMemsetAsync(s, 0, sizeof(double), g_stream));
+  g_launches++;
+  if (L.nboxes > 0) {
+    const int pairs = (L.dim / 2) * L.dim * L.dim;
+    int bx = (pairs + 1023) / 1024;
+    if (bx > 592) bx = 592;
+    LAUNCH(copy_norm_kernel, dim3(bx, L.nboxes), 256, 0, L, id_c, id_a, s);
+  }
+  hpgmg_comm_allreduce_slot_max(level, slot);
+}
+
 extern "C" void hpgmg_norm_async(level_type *level, int id_a, int slot)
 {
   ProfileScope prof_(&level->timers.blas1);

@@ -26,6 +26,7 @@ struct StencilArgs {
   int diag;                /* TMA GSRB kernel: form Dinv = 1/Aii in registers from the face coefficients wherever the stencil
                               stays clear of the boundary-condition ghost cells (the stored Dinv holds exactly that there) */
   int dom[3];              /* level dimensions in cells */
+  double *norm_slot;       /* TMA residual kernel: also leave max |res| here (the norm the caller wants next), or NULL */
   int l2hint;              /* TMA kernel: keep the face coefficients in L2 (evict_last); 2: and stream x (evict_first) */
 };
 
@@ -199,6 +200,8 @@ static const TileMaps *tile_maps(const DLevel &L, const int w, const int xr, con
   return M;
 }
 
+static bool g_norm_fused = false;          /* did the last residual launch also produce the norm? */
+
 template <int OP, int TI, int TJ, int PF, int MINB>
 static void launch_tma(const StencilArgs &A)
 {
@@ -224,6 +227,7 @@ static void launch_tma(const StencilArgs &A)
   if (g_tma_chunks > 0) chunks = g_tma_chunks;
   while (n % chunks) chunks--;
   long long blocks = g_tma_blocks > 0 ? g_tma_blocks : columns * chunks;
+  if (OP == OP_RESIDUAL && A.norm_slot) g_norm_fused = true;
   if (A.reverse && OP == OP_GSRB) LAUNCH((stencil_tma_kernel<OP, TI, TJ, PF, MINB, (OP == OP_GSRB)>), dim3((unsigned)blocks), dim3(C::NT), C::SMEM, A, M->x, M->b, total);
   else                            LAUNCH((stencil_tma_kernel<OP, TI, TJ, PF, MINB, false>), dim3((unsigned)blocks), dim3(C::NT), C::SMEM, A, M->x, M->b, total);
 }
@@ -356,6 +360,24 @@ extern "C" void residual(level_type *level, int res_id, int x_id, int rhs_id, do
   StencilArgs A = {};
   A.x_id = x_id;  A.rhs_id = rhs_id;  A.out_id = res_id;  A.a = a;  A.b = b;
   launch_stencil<OP_RESIDUAL>(level, A);
+}
+
+/* residual() followed by norm() of the result (mg.c:1316-1322, 1259-1262), the max taken inside the residual kernel
+ * where that kernel is the TMA one: saves re-reading the residual (8 B/cell and a launch).  max is order-free. */
+extern "C" void hpgmg_residual_norm_async(level_type *level, int res_id, int x_id, int rhs_id, double a, double b, int slot)
+{
+  static int fuse = -1;
+  if (fuse < 0) { const char *e = getenv("HPGMG_B200_FUSE_NORM"); fuse = e ? atoi(e) : 1; }
+  if (!fuse || hpgmg_rt_profile()) { residual(level, res_id, x_id, rhs_id, a, b); hpgmg_norm_async(level, res_id, slot); return; }
+  fill_ghosts(level, x_id);
+  double *s = hpgmg_rt_scalar_slots() + slot;
+  CUDA_CHECK(cudaMemsetAsync(s, 0, sizeof(double), g_stream));
+  StencilArgs A = {};
+  A.x_id = x_id;  A.rhs_id = rhs_id;  A.out_id = res_id;  A.a = a;  A.b = b;  A.norm_slot = s;
+  g_norm_fused = false;
+  launch_stencil<OP_RESIDUAL>(level, A);
+  if (g_norm_fused) hpgmg_comm_allreduce_slot_max(level, slot);     /* MPI_Allreduce(MAX), misc.c:324; no-op on one rank */
+  else hpgmg_norm_async(level, res_id, slot);
 }
 
 static void smooth_gsrb(level_type *level, int x_id, int rhs_id, double a, double b)

@@ -150,6 +150,7 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
   const long long lo = total_planes * (long long)blockIdx.x / (long long)gridDim.x;
   const long long hi = total_planes * (long long)(blockIdx.x + 1) / (long long)gridDim.x;
   unsigned phasebits = 0;                                           /* bit q: parity of the next wait on mbarrier q */
+  double vmax = 0.0;                                                /* OP_RESIDUAL: max |res| over this thread's cells */
 
   for (long long pos = lo; pos < hi;) {
     const int col = (int)(pos / n);
@@ -293,7 +294,7 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
           const double Ax = fv4_apply_op_at(X, BI, BJ, BK, A.b, A.h2inv);
           double v;
           if (OP == OP_APPLY) v = Ax;
-          else if (OP == OP_RESIDUAL) v = (c ? rhs2.y : rhs2.x) - Ax;
+          else if (OP == OP_RESIDUAL) { v = (c ? rhs2.y : rhs2.x) - Ax; const double f = fabs(v); if (f > vmax) vmax = f; }
           else {                                                     /* OP_CHEBY, chebyshev.c:90 */
             const double xn = X(0, 0, 0);
             v = xn + A.c1 * (xn - (c ? xm2.y : xm2.x)) + A.c2 * (c ? dinv2.y : dinv2.x) * ((c ? rhs2.y : rhs2.x) - Ax);
@@ -315,6 +316,14 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
       __syncthreads();                                               /* everyone is done with the oldest slots */
     }
 #undef PLANE_NEEDS_DINV
+  }
+  if (OP == OP_RESIDUAL && A.norm_slot != nullptr) {                /* norm(): misc.c:287-329, max of |res| */
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double other = __shfl_down_sync(0xffffffffu, vmax, o);
+      if (other > vmax) vmax = other;
+    }
+    if (lane == 0) atomic_max_nonneg(A.norm_slot, vmax);
   }
 }
 

@@ -252,6 +252,73 @@ __global__ void __launch_bounds__(256) interpolation_tiled_kernel(const DLevel L
   }
 }
 
+/* The same arithmetic again, marching along k: a thread owns one (i, j) column of coarse cells of a list entry.
+ * Per coarse PLANE it loads the W x W values around its column once, runs the i- and j-passes (W + 2 one-
+ * dimensional prolongations) and pushes the four (fine i, fine j) results into a W-deep register window; the k-pass
+ * of coarse cell k then reads that window.  A coarse cell costs W*W loads and W+2+4 prolongations instead of
+ * W*W*W loads and W*W+2W+4 (the tiled kernel above is LSU-bound on exactly those loads); the W-1 planes of run-in
+ * are paid once per entry (8 planes deep, mg.c:274-277).  Lanes run along i, so the loads are coalesced rows
+ * straight through L1.  Same prolong3/prolong5 calls on the same operands in the same order: same bits. */
+template <int W>
+__global__ void __launch_bounds__(256) interpolation_march_kernel(const DLevel Lf, const int id_f, const double prescale,
+                                                                  const DLevel Lc, const int id_c,
+                                                                  const blockCopy_type *__restrict__ blocks)
+{
+  PDL_WAIT();
+  constexpr int R = W / 2;
+  const blockCopy_type B = blocks[blockIdx.x];
+  const int di = B.dim.i, dj = B.dim.j, dk = B.dim.k;
+  const int col = blockIdx.y * blockDim.x + threadIdx.x;
+  if (col >= di * dj) return;
+  const int ii = col % di, jj = col / di;
+  const int rj = Lc.jStride, rk = Lc.kStride, wj = Lf.jStride, wk = Lf.kStride;
+  const double *__restrict__ r = Lc.vec(B.read.box, id_c) + (B.read.i + ii) + (B.read.j + jj) * rj + (B.read.k - R) * rk;   /* plane k-R of the column */
+  double *w = Lf.vec(B.write.box, id_f) + (2 * ii + B.write.i) + (2 * jj + B.write.j) * wj + B.write.k * wk;
+  const bool vec2 = ((B.write.i & 1) == 0);
+  double win[2][2][W];                                            /* [fine i][fine j][coarse plane k-R .. k+R] */
+#pragma unroll 1
+  for (int K = 0; K < dk + 2 * R; K++, r += rk) {
+    /* i-pass on the W rows of this coarse plane, then the j-pass */
+    double fi[2][W];
+#pragma unroll
+    for (int J = 0; J < W; J++) {
+      const double *p = r + (J - R) * rj;
+      if constexpr (W == 3) prolong3(p[-1], p[0], p[1], fi[0][J], fi[1][J]);
+      else                  prolong5(p[-2], p[-1], p[0], p[1], p[2], fi[0][J], fi[1][J]);
+    }
+#pragma unroll
+    for (int I = 0; I < 2; I++) {
+#pragma unroll
+      for (int q = 0; q < W - 1; q++) { win[I][0][q] = win[I][0][q + 1]; win[I][1][q] = win[I][1][q + 1]; }
+      if constexpr (W == 3) prolong3(fi[I][0], fi[I][1], fi[I][2], win[I][0][W - 1], win[I][1][W - 1]);
+      else                  prolong5(fi[I][0], fi[I][1], fi[I][2], fi[I][3], fi[I][4], win[I][0][W - 1], win[I][1][W - 1]);
+    }
+    if (K < 2 * R) continue;                                      /* window not full yet */
+    /* k-pass for coarse cell K-2R and commit its 8 fine cells */
+    double *w0 = w + 2 * (K - 2 * R) * wk;
+#pragma unroll
+    for (int J = 0; J < 2; J++) {
+      double lo[2], hi[2];
+#pragma unroll
+      for (int I = 0; I < 2; I++) {
+        if constexpr (W == 3) prolong3(win[I][J][0], win[I][J][1], win[I][J][2], lo[I], hi[I]);
+        else                  prolong5(win[I][J][0], win[I][J][1], win[I][J][2], win[I][J][3], win[I][J][4], lo[I], hi[I]);
+      }
+      double *wr = w0 + J * wj;
+      if (vec2) {
+        double2 a = *reinterpret_cast<double2 *>(wr), b2 = *reinterpret_cast<double2 *>(wr + wk);
+        a.x = prescale * a.x + lo[0];   a.y = prescale * a.y + lo[1];
+        b2.x = prescale * b2.x + hi[0]; b2.y = prescale * b2.y + hi[1];
+        *reinterpret_cast<double2 *>(wr) = a;
+        *reinterpret_cast<double2 *>(wr + wk) = b2;
+      } else {
+        wr[0] = prescale * wr[0] + lo[0];        wr[1] = prescale * wr[1] + lo[1];
+        wr[wk] = prescale * wr[wk] + hi[0];      wr[wk + 1] = prescale * wr[wk + 1] + hi[1];
+      }
+    }
+  }
+}
+
 /* fine-level unpack of prolonged data received from another rank: write = prescale*write + recv
  * (IncrementBlock, blockCopy.c:108-156) */
 __global__ void __launch_bounds__(128) increment_blocks_kernel(const DLevel L, const int id, const double prescale, const blockCopy_type *__restrict__ blocks)
@@ -294,7 +361,12 @@ static void interpolation_driver(level_type *level_f, int id_f, double prescale_
     const int half = level_f->box_dim / 2;
     const int di = half, dj = half < BLOCKCOPY_TILE_J ? half : BLOCKCOPY_TILE_J, dk = half < BLOCKCOPY_TILE_K ? half : BLOCKCOPY_TILE_K;
     const int subtiles = ((di + 31) / 32) * ((dj + 3) / 4) * ((dk + 1) / 2);
-    LAUNCH(interpolation_tiled_kernel<W>, dim3(local.n, subtiles), dim3(32, 4, 2), 0, Df->L, id_f, prescale_f, Dc->L, id_c, local.blocks);
+    static int march = -1;
+    if (march < 0) { const char *e = getenv("HPGMG_B200_INTERP_MARCH"); march = e ? atoi(e) : 512; }   /* minimum columns per entry: the planes of a column are sequential, small levels need the width */
+    if (march && dk >= 4 && di * dj >= march)
+      LAUNCH(interpolation_march_kernel<W>, dim3(local.n, (di * dj + 255) / 256), dim3(256), 0, Df->L, id_f, prescale_f, Dc->L, id_c, local.blocks);
+    else
+      LAUNCH(interpolation_tiled_kernel<W>, dim3(local.n, subtiles), dim3(32, 4, 2), 0, Df->L, id_f, prescale_f, Dc->L, id_c, local.blocks);
   }
   if (remote) {
     hpgmg_comm_transfer_wait(level_c, Cc, level_f, Cf);

@@ -543,8 +543,7 @@ static void enqueue_residual_norm(level_type *L, int e_id, int F_id, double a, d
     double average = mean(L, e_id);                     /* synchronises: periodic problems are not graph-captured */
     shift_vector(L, e_id, e_id, -average);
   }
-  residual(L, VECTOR_TEMP, e_id, F_id, a, b);
-  hpgmg_norm_async(L, VECTOR_TEMP, HPGMG_SLOT_NORM_R);
+  hpgmg_residual_norm_async(L, VECTOR_TEMP, e_id, F_id, a, b, HPGMG_SLOT_NORM_R);
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -554,8 +553,7 @@ static void enqueue_residual_norm(level_type *L, int e_id, int F_id, double a, d
 static void enqueue_fcycle(mg_type *MG, int onLevel, int e_id, int R_id, int F_id, double a, double b)
 {
   level_type *L = MG->levels[onLevel];
-  hpgmg_norm_async(L, F_id, HPGMG_SLOT_NORM_F);
-  scale_vector(L, R_id, 1.0, F_id);
+  hpgmg_copy_norm_async(L, R_id, F_id, HPGMG_SLOT_NORM_F);
   for (int l = onLevel; l < MG->num_levels - 1; l++)
     restriction(MG->levels[l + 1], R_id, MG->levels[l], R_id, RESTRICT_CELL);
   int bottom = MG->num_levels - 1;

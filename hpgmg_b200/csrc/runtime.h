@@ -64,6 +64,8 @@ void    hpgmg_rt_read_scalars(double *host, int first, int count); /* sync + cop
 
 /* async reductions that leave their result in a scalar slot (no host sync) */
 void hpgmg_norm_async(level_type *level, int id_a, int slot);
+void hpgmg_copy_norm_async(level_type *level, int id_c, int id_a, int slot);          /* norm(a) and c = 1.0*a in one pass */
+void hpgmg_residual_norm_async(level_type *level, int res_id, int x_id, int rhs_id, double a, double b, int slot);  /* residual, then its norm */
 
 /* on-device bottom solver; returns 0 if the level is not eligible (caller falls back to the
  * host-driven BiCGStab in solvers.c) */
