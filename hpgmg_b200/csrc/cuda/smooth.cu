@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(const StencilArgs 
 #include "stencil_tma.cuh"
 #include <vector>
 
-static int g_tiled_async = 1, g_tma = 1, g_tma_blocks = 0, g_tma32 = 1, g_zigzag = 1, g_tma_chunks = 0, g_tma_cfg = 2, g_tma_cfg_full = 2, g_diag = 1, g_l2hint = 0, g_l2hint_mb = 100, g_persistent_maxdim = 16;
+static int g_tiled_async = 1, g_tma = 1, g_tma_blocks = 0, g_tma32 = 1, g_zigzag = 1, g_tma_chunks = 0, g_tma_cfg = 2, g_tma_cfg_full = 2, g_tma_cfg32 = 2, g_tma_minplanes = 8, g_diag = 1, g_l2hint = 0, g_l2hint_mb = 100, g_persistent_maxdim = 16;
 static int g_force_generic = -1, g_kchunk_override = -1, g_tile32 = 0, g_min_chunk = 16, g_persistent_smooth = 0, g_pair_kernel = 1;
 
 static void stencil_env(void)
@@ -123,6 +123,10 @@ static void stencil_env(void)
     if (dg) g_diag = atoi(dg);
     const char *cf = getenv("HPGMG_B200_TMA_CFG");
     if (cf) g_tma_cfg = g_tma_cfg_full = atoi(cf);
+    const char *c3 = getenv("HPGMG_B200_TMA_CFG32");         /* boxes of 32^3: one block per SM at most, so latency rules */
+    if (c3) g_tma_cfg32 = atoi(c3);
+    const char *mp = getenv("HPGMG_B200_TMA_MINPLANES");
+    if (mp) g_tma_minplanes = atoi(mp);
     const char *cr = getenv("HPGMG_B200_TMA_CFG_FULL");      /* the operators that evaluate every cell: residual, Chebyshev, apply_op */
     if (cr) g_tma_cfg_full = atoi(cr);
     const char *t3 = getenv("HPGMG_B200_TMA32");
@@ -222,7 +226,7 @@ static void launch_tma(const StencilArgs &A)
    * slots (MINB blocks per SM) and keeps >= 8 planes per block. */
   const long long slots = (long long)MINB * hpgmg_rt_sm_count(), columns = total / n;
   long long chunks = slots / columns;
-  if (chunks > n / 8) chunks = n / 8;
+  if (chunks > n / g_tma_minplanes) chunks = n / g_tma_minplanes;
   if (chunks < 1) chunks = 1;
   if (g_tma_chunks > 0) chunks = g_tma_chunks;
   while (n % chunks) chunks--;
@@ -245,6 +249,7 @@ static bool launch_tma_cfg(const StencilArgs &A, const int cfg)
     case 4: if (n % 32) return false; launch_tma<OP, 32, 8, 2, 3>(A); return true;
     case 5: if (n % 32) return false; launch_tma<OP, 32, 16, 1, 2>(A); return true;
     case 6: if (n % 64) return false; launch_tma<OP, 64, 16, 1, 1>(A); return true;
+    case 7: if (n % 32) return false; launch_tma<OP, 32, 8, 3, 2>(A); return true;
     default: return false;
   }
 }
@@ -316,7 +321,7 @@ static void launch_stencil(level_type *level, StencilArgs &A)
   if (OP != OP_REBUILD && !g_force_generic) {
     if (n % 32 == 0 && n >= 64 && (g_tile32 == 2 || (g_tile32 == 1 && n == 64))) { launch_tiled<OP, 32, 8>(A); return; }
     if (n >= 64 && g_tma && launch_tma_cfg<OP>(A, OP == OP_GSRB ? g_tma_cfg : g_tma_cfg_full)) return;
-    if (n == 32 && g_tma32 && launch_tma_cfg<OP>(A, 2)) return;
+    if (n == 32 && g_tma32 && launch_tma_cfg<OP>(A, g_tma_cfg32)) return;
     if (n % 64 == 0) { launch_tiled<OP, 64, 8>(A); return; }
     if ((n & 1) == 0 && n >= 4 && g_pair_kernel) {
       const int hn = n / 2;
