@@ -90,7 +90,7 @@ _REF_SYMBOLS = ["create_level", "destroy_level", "create_vectors", "reset_level_
                 "interpolation_v2", "interpolation_v4", "exchange_boundary", "apply_BCs", "apply_BCs_v1", "apply_BCs_v2",
                 "apply_BCs_v4", "extrapolate_betas", "dot", "norm", "mean", "error", "add_vectors", "scale_vector",
                 "zero_vector", "shift_vector", "mul_vectors", "invert_vector", "init_vector", "color_vector",
-                "random_vector", "initialize_problem", "evaluateBeta", "evaluateF", "MGBuild", "MGSolve", "FMGSolve",
+                "random_vector", "initialize_problem", "evaluateBeta", "evaluateF", "MGBuild", "MGSolve", "FMGSolve", "FMGSolve2", "MGPCG",
                 "MGVCycle", "MGDestroy", "MGResetTimers", "richardson_error", "IterativeSolver", "IterativeSolver_NumVectors"]
 
 

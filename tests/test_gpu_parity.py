@@ -361,6 +361,44 @@ def test_multi_gpu_fmg_equals_single_process_reference(gpu_lib, ranks):
     assert "PARITY OK (bit-exact)" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+# ------------------------------------------------------------------------- the other solve drivers of mg.c
+@pytest.mark.skipif(not ob.have_ref(), reason="oracle/_ref (prebuilt reference library) not shipped")
+@pytest.mark.parametrize("driver", ["MGSolve", "FMGSolve2", "MGPCG"])
+def test_other_solve_drivers_equal_reference(gpu_lib, driver):
+    """MGSolve (V-cycles to rtol, mg.c:1168-1233), FMGSolve2 (mg.c:1348-1495) and MGPCG (mg.c:1500-1607) are part of the
+    API surface of the path: same solution as the reference library, cell by cell.  The reference
+    runs on one OpenMP thread: MGPCG's dots are sums over tiles whose order is only defined there."""
+    with api.Hierarchy(5, 8, verbose=False) as H:
+        R = ob.RefHierarchy(5, 8)
+        with ob.ref_threads(1):
+            R.call("zero_vector", R.level(0), api.VECTOR_U)
+            R.call(driver, R.mg, 0, api.VECTOR_U, api.VECTOR_F, 0.0, 1.0, 1e-10)
+        gpu_lib.zero_vector(H.level(0), api.VECTOR_U)
+        getattr(gpu_lib, driver)(H.mg, 0, api.VECTOR_U, api.VECTOR_F, 0.0, 1.0, 1e-10)
+        gpu_lib.hpgmg_b200_sync()
+        assert_level_equal(H, R, 0, api.VECTOR_U, "in", driver)
+
+
+def test_operator_timers_fill_the_reference_table(gpu_lib, capfd):
+    """hpgmg_b200_profile_operators(1): every operator adds its time to level->timers.* like the reference's getTime()
+    brackets, so MGPrintTiming prints the reference's table; the solve itself must not change."""
+    g = ob.goldens()["solves"]["5 8 gsrb"]
+    with api.Hierarchy(5, 8, verbose=False) as H:
+        gpu_lib.hpgmg_b200_profile_operators(1)
+        try:
+            gpu_lib.MGResetTimers(H.mg)
+            r, _ = H.fmg_solve(0)
+            t = H.level(0).contents.timers
+            assert r == g["norms"][0]
+            assert t.smooth > 0.0 and t.residual > 0.0 and t.restriction_total > 0.0 and t.interpolation_total > 0.0 and t.ghostZone_total > 0.0
+            gpu_lib.MGPrintTiming(H.mg, 0)
+        finally:
+            gpu_lib.hpgmg_b200_profile_operators(0)
+    C.CDLL(None).fflush(None)
+    out = capfd.readouterr().out
+    assert "smooth" in out and "residual" in out and "Total by level" in out
+
+
 # ------------------------------------------------------------------------- kernel variants behind switches
 VARIANTS = [
     {"HPGMG_B200_TMA_CFG": "0"},                                  # 64x8 tiles, 2 blocks/SM
