@@ -48,6 +48,7 @@ SIGNATURES = {
     "hpgmg_upload_box_vector": (_V, [_LP, _I, _I, C.c_void_p]),
     "hpgmg_b200_host_alloc_pinned": (C.c_void_p, [C.c_size_t]), "hpgmg_b200_host_free_pinned": (_V, [C.c_void_p]),
     "hpgmg_fmg_solve_host": (_D, [_MP, _I, _I, _I, _D, _D, _D, C.c_void_p, C.c_void_p]),
+    "hpgmg_fmg_solve_host_bytes": (C.c_ulonglong, [_MP, _I]),
     "hpgmg_last_norm_of_F": (_D, [_MP]), "hpgmg_last_norm_of_residual": (_D, [_MP]),
     "hpgmg_last_richardson_error": (_D, []), "hpgmg_last_richardson_order": (_D, []),
     "hpgmg_b200_kernel_launches": (C.c_ulonglong, []), "hpgmg_b200_device_seconds_last_solve": (_D, []),

@@ -103,6 +103,7 @@ def test_fmg_solve_host_buffers(gpu_lib):
         r2 = gpu_lib.hpgmg_fmg_solve_host(H.mg, 0, api.VECTOR_U, api.VECTOR_F, 0.0, 1.0, 1e-10, f.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p))
         assert r2 == r
         np.testing.assert_array_equal(u, u_ref)
+        assert gpu_lib.hpgmg_fmg_solve_host_bytes(H.mg, 0) == nb * vol * 8
 
 
 # ------------------------------------------------------------------------------ operator by operator
