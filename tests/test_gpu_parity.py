@@ -417,6 +417,10 @@ VARIANTS = [
     {"HPGMG_B200_PERSISTENT_SMOOTH": "8"},                        # small levels: one smooth = one cluster kernel
     {"HPGMG_B200_PERSISTENT_SMOOTH": "1"},                        # ... cooperative grid barrier
     {"HPGMG_B200_NO_COARSE_KERNEL": "1"},
+    {"HPGMG_B200_TMA_CFG": "7"},                                  # 32x8, three steps ahead
+    {"HPGMG_B200_FUSE_NORM": "0"},                                # norm as a separate kernel after residual / R=F
+    {"HPGMG_B200_INTERP_MARCH": "0"},                             # tiled interpolation on every level
+    {"HPGMG_B200_INTERP_MARCH": "64"},                            # k-marching interpolation down to 16^3 boxes
 ]
 
 
