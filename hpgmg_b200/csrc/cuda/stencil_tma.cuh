@@ -1,7 +1,6 @@
 /*
- * stencil_tma.cuh -- the operator kernels for boxes >= 32^3, Blackwell version: 2.5-D blocking, the
- * halo tiles staged in shared memory by the TMA engine, a persistent grid with an even split of the
- * (box, tile, k) work space.
+ * stencil_tma.cuh -- the operator kernels for boxes >= 32^3, Blackwell version: 2.5-D blocking with the halo
+ * tiles staged in shared memory by the TMA engine.
  *
  * What it computes is what stencil_tiled.cuh computes (GSRB / Chebyshev / residual / apply_op on a
  * TI x TJ column of cells marching along k; gsrb.c:41-129, chebyshev.c:51-97, residual.c:18-49,
@@ -9,18 +8,23 @@
  * fv4_apply_op_at, hence the same bits.  What changed is everything around the arithmetic:
  *
  *  - staging: one elected thread issues cp.async.bulk.tensor (TMA) copies of whole (TI+4) x rows tiles
- *    of x, beta_i, beta_j, beta_k for the next plane into ring buffers; completion is counted by an
- *    mbarrier (complete_tx::bytes).  No LDGSTS / address arithmetic in the 8 compute warps (the
- *    cp.async version spent 16 LDGSTS = 128 LSU cycles per warp and plane on it).
+ *    of x, beta_i, beta_j, beta_k PF steps ahead into ring buffers; completion is counted by mbarriers
+ *    (complete_tx::bytes).  No LDGSTS / address arithmetic in the compute warps (the cp.async version
+ *    spent 16 LDGSTS = 128 LSU cycles per warp and plane on it).
  *  - layout: rows are stored as they are in memory (TMA cannot split parities).  Bank conflicts of the
  *    stride-2 red-black accesses are avoided by the lane mapping instead: even lanes work on row r, odd
  *    lanes on row r+1 of a row pair; the active cells of the two rows have opposite i-parity, so the 16
  *    lanes of a half-warp touch 16 distinct 8-byte banks.
  *  - addressing: a lane keeps ONE 32-bit shared address per ring slot (its active cell); every stencil
  *    operand is a load at a compile-time offset from it (LDS [R+imm]).
- *  - scheduling: grid = resident blocks (2 per SM); block b owns the planes [P*b/G, P*(b+1)/G) of the
- *    linearised (box, tile, k) space, so all SMs finish together (the fixed k-chunk grid of the cp.async
- *    kernel ran 1.73 waves on `7 8`).
+ *  - scheduling: block b owns the planes [P*b/G, P*(b+1)/G) of the linearised (box, tile, k) space and
+ *    walks them as segments of one column each.  The launcher (smooth.cu: launch_tma) picks G = columns x
+ *    equal k-chunks, so that every block is exactly one chunk and all blocks march k in step; any other G
+ *    (HPGMG_B200_TMA_BLOCKS) gives an even split with partial columns -- correct, but 24 % slower on `7 8`
+ *    because neighbouring tiles then fetch their common halo rows at different times.
+ *  - GSRB only: Dinv = 1/Aii is formed from the face coefficients in registers away from the domain boundary
+ *    (stencil.cuh) instead of being read; alternate sweeps march k downwards (REV).
+ *  - residual only: the kernel also leaves max |res| in a scalar slot when the caller wants the norm next.
  */
 #ifndef HPGMG_B200_STENCIL_TMA_CUH
 #define HPGMG_B200_STENCIL_TMA_CUH
