@@ -145,6 +145,10 @@ struct hpgmg_device_level {
   DList  interpolation[3];
   FillTable fill[STENCIL_MAX_SHAPES];
   int fill_nvec;                                /* numVectors the fill offsets were built for */
+  int dinv_is_unit_diagonal;                    /* VECTOR_DINV was last written by rebuild_operator_blackbox with >= 4 colours per
+                                                   dimension (no two cells of a colour inside one stencil): away from the boundary it
+                                                   then holds exactly 1/(A applied to the unit vector), which the GSRB kernel may
+                                                   recompute instead of reading.  Cleared when somebody else writes the vector. */
   double *tile_partials;                        /* scratch for dot/mean: one double per compute tile */
   blockCopy_type *tiles;                        /* device copy of level->my_blocks                  */
   int     ntiles;

@@ -202,6 +202,7 @@ extern "C" void hpgmg_upload_box_vector(level_type *level, int box, int id, cons
   const box_type *B = &level->my_boxes[box];
   hpgmg_rt_copy_h2d(B->vectors[id], host, (size_t)B->volume * sizeof(double));
   hpgmg_rt_sync();
+  if (id == VECTOR_DINV && HPGMG_DEV(level)) HPGMG_DEV(level)->dinv_is_unit_diagonal = 0;      /* a caller-supplied diagonal is read, not recomputed */
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -314,7 +314,7 @@ static void launch_stencil(level_type *level, StencilArgs &A)
   /* the identity behind `diag` needs the 4^3-colour black-box diagonal (rebuild_operator, operators.fv4.c:145-173:
    * no two cells of a colour within one stencil) and Dirichlet ghost cells that only cells within 2 of the
    * boundary can see */
-  A.diag = (OP == OP_GSRB && g_diag && level->boundary_condition.type == BC_DIRICHLET && level->dim.i >= 8 && level->dim.j >= 8 && level->dim.k >= 8) ? 1 : 0;
+  A.diag = (OP == OP_GSRB && g_diag && HPGMG_DEV(level)->dinv_is_unit_diagonal && level->boundary_condition.type == BC_DIRICHLET && level->dim.i >= 8 && level->dim.j >= 8 && level->dim.k >= 8) ? 1 : 0;
   const int n = L.dim;
   stencil_env();
   if (OP != OP_REBUILD && hpgmg_ablate(n < 64 ? 8 : (OP == OP_RESIDUAL ? 32 : 64))) return;
@@ -633,6 +633,7 @@ extern "C" void rebuild_operator_blackbox(level_type *level, double a, double b,
   if (chatty) fprintf(stdout, "done\n");
   if (chatty && hpgmg_rt_smoother() == HPGMG_SMOOTHER_CHEBY) { fprintf(stdout, "  estimating  lambda_max... <%1.15e\n", eig); fflush(stdout); }
   level->dominant_eigenvalue_of_DinvA = eig;
+  HPGMG_DEV(level)->dinv_is_unit_diagonal = (colors_in_each_dim >= 4) ? 1 : 0;
 }
 
 extern "C" void rebuild_operator(level_type *level, level_type *fromLevel, double a, double b)
