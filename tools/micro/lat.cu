@@ -1,4 +1,6 @@
-// latency micro-benchmarks on one warp: dependent DADD / DMUL chains, integer division, generic vs shared loads
+// latency micro-benchmarks on one warp: dependent DADD / DMUL chains, integer division, generic loads from shared memory
+// build + run: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -o tools/micro/lat tools/micro/lat.cu && tools/micro/lat
+// measured on B200: DADD 9.0, DMUL 8.4 cycles dependent-issue latency; runtime integer division 79-118; generic LD (shared) + DADD + cvt 67
 #include <cstdio>
 #include <cuda_runtime.h>
 __global__ void k(double *out, long long *cyc, int n, int div)
