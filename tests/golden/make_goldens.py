@@ -2,7 +2,8 @@
 """Regenerate tests/golden/goldens.json from the UNMODIFIED reference (oracle/_ref, built by
 oracle/Makefile from /root/reference/finite-volume/source with gcc -O2 -fopenmp, no FMA).
 
-  python tests/golden/make_goldens.py
+  python tests/golden/make_goldens.py            # only what is missing from goldens.json
+  python tests/golden/make_goldens.py --all      # everything again
 
 Recorded per solve configuration (`hpgmg-fv <log2_box_dim> <boxes>` on one rank; an N-rank run has
 the same boxes and therefore the same numbers): the F-cycle residual norms of the
@@ -22,6 +23,7 @@ import hpgmg_b200.api as api  # noqa: E402
 
 SOLVES = [(4, 1, False), (5, 1, False), (6, 1, False), (4, 8, False), (5, 8, False), (6, 8, False), (7, 8, False),
           (4, 27, False), (5, 27, False), (5, 64, False),
+          (7, 27, False), (7, 64, False),      # = `7 8` per GPU on 4 / 8 GPUs (384^3 and 512^3: 4.5 and 10.6 GB on the host)
           (5, 1, True), (5, 8, True), (6, 8, True), (5, 27, True)]
 DECOMPOSITIONS = [(5, 8, 1), (5, 8, 2), (5, 8, 4), (5, 8, 8), (4, 1, 1), (6, 8, 1), (6, 8, 8), (4, 3, 9)]
 
@@ -64,12 +66,20 @@ def main():
     assert ob.have_ref() and ob.have_ref(True), "build oracle/_ref first: make -C oracle ref"
     G = {"generator": "tests/golden/make_goldens.py", "reference_flags": "gcc -O2 -fopenmp -std=gnu99 -DUSE_BICGSTAB=1 -DUSE_SUBCOMM=1 -DUSE_FCYCLES=1 -DUSE_{GSRB,CHEBY}=1 (x86-64 baseline: no FMA)",
          "solves": {}, "decompositions": {}}
+    path = os.path.join(HERE, "goldens.json")
+    if "--all" not in sys.argv and os.path.exists(path):
+        with open(path) as f:
+            G = json.load(f)
     for log2, boxes, cheby in SOLVES:
         key = f"{log2} {boxes} {'cheby' if cheby else 'gsrb'}"
+        if key in G["solves"]:
+            continue
         print("solve", key, flush=True, file=sys.stderr)
         G["solves"][key] = solve_record(log2, boxes, cheby)
     for log2, bpr, ranks in DECOMPOSITIONS:
         key = f"{log2} {bpr} x{ranks}"
+        if key in G["decompositions"]:
+            continue
         print("decomposition", key, flush=True, file=sys.stderr)
         G["decompositions"][key] = decomposition_record(log2, bpr, ranks)
     with open(os.path.join(HERE, "goldens.json"), "w") as f:
