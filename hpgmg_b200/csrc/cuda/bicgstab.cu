@@ -24,17 +24,29 @@ __global__ void __launch_bounds__(BOTTOM_THREADS) bicgstab_kernel(const BottomAr
 /* Returns 1 if the solve was enqueued on the device, 0 if the level is not eligible (more than one
  * box on this rank, other ranks involved, a periodic problem that needs mean subtraction, or a box
  * larger than the kernel's shared-memory staging) and the caller must use the host-driven loop. */
-extern "C" int hpgmg_bicgstab_device(level_type *level, int x_id, int R_id, double a, double b, double rtol)
+/* side-effect free: would hpgmg_bicgstab_device() take this level?  (mg.c uses it to decide whether a solve can be
+ * recorded into a CUDA graph: the host-driven fallback synchronises on every dot / norm) */
+extern "C" int hpgmg_bicgstab_device_eligible(const level_type *level)
 {
   if (level->must_subtract_mean == 1) return 0;
   if (level->boundary_condition.type != BC_DIRICHLET) return 0;
   if (level->num_my_boxes != 1) return 0;
   if (level->boxes_in.i != 1 || level->boxes_in.j != 1 || level->boxes_in.k != 1) return 0;
   if (level->box_dim > BOTTOM_MAX_DIM || level->box_dim < 2) return 0;
+  if (level->box_ghosts != 2) return 0;
+  const hpgmg_device_level *D = HPGMG_DEV(level);
+  /* the fill tables are rebuilt for the new vector count when IterativeSolver grows the level (create_vectors) */
+  if (D->fill_nvec == 0 || D->fill[STENCIL_SHAPE_NO_CORNERS].nlate > 0) return 0;
+  return 1;
+}
+
+extern "C" int hpgmg_bicgstab_device(level_type *level, int x_id, int R_id, double a, double b, double rtol)
+{
+  if (!hpgmg_bicgstab_device_eligible(level)) return 0;
   hpgmg_device_level *D = HPGMG_DEV(level);
   BottomArgs A;
   A.L = D->L;
-  if (D->fill_nvec != level->numVectors || D->fill[STENCIL_SHAPE_NO_CORNERS].nlate > 0) return 0;
+  if (D->fill_nvec != level->numVectors) return 0;
   A.bc = D->fill[STENCIL_SHAPE_NO_CORNERS].bc;  A.nbc = D->fill[STENCIL_SHAPE_NO_CORNERS].nbc;
   A.x_id = x_id;  A.R_id = R_id;  A.a = a;  A.b = b;
   A.h2inv = 1.0 / (level->h * level->h);

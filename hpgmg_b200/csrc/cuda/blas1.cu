@@ -78,6 +78,7 @@ template <int OP>
 static void launch_blas1(level_type *level, BlasArgs &A)
 {
   if (hpgmg_ablate(128)) return;
+  hpgmg_note_vector_written(level, A.c);
   const DLevel &L = dl_of(level);
   if (L.nboxes == 0) return;
   A.L = L;

@@ -360,8 +360,8 @@ extern "C" void hpgmg_b200_coarse_profile(int on, long long *out9)
 }
 /* single-block cycles pay off up to 8^3 (one cell per thread, latency-bound); 16^3 is faster as separate launches */
 static long g_coarse_max_cells = 512;
-extern "C" void hpgmg_b200_coarse_levels_in_smem(int on) { g_coarse_smem = on ? 1 : 0; }
-extern "C" void hpgmg_b200_use_coarse_kernel(int on) { g_coarse_enabled = on ? 1 : 0; }
+extern "C" void hpgmg_b200_coarse_levels_in_smem(int on) { if ((on ? 1 : 0) != g_coarse_smem) hpgmg_graph_drop_all(NULL); g_coarse_smem = on ? 1 : 0; }
+extern "C" void hpgmg_b200_use_coarse_kernel(int on) { if ((on ? 1 : 0) != g_coarse_enabled) hpgmg_graph_drop_all(NULL); g_coarse_enabled = on ? 1 : 0; }
 
 static int level_is_coarse_eligible(const level_type *level, int is_top, int is_bottom)
 {

@@ -148,7 +148,8 @@ struct hpgmg_device_level {
   int dinv_is_unit_diagonal;                    /* VECTOR_DINV was last written by rebuild_operator_blackbox with >= 4 colours per
                                                    dimension (no two cells of a colour inside one stencil): away from the boundary it
                                                    then holds exactly 1/(A applied to the unit vector), which the GSRB kernel may
-                                                   recompute instead of reading.  Cleared when somebody else writes the vector. */
+                                                   recompute instead of reading.  Cleared by every other writer of the vector
+                                                   (hpgmg_note_vector_written: BLAS1, transfers, smoothers, uploads). */
   double *tile_partials;                        /* scratch for dot/mean: one double per compute tile */
   blockCopy_type *tiles;                        /* device copy of level->my_blocks                  */
   int     ntiles;
@@ -188,6 +189,15 @@ static inline int hpgmg_ablate(const int bit)
 }
 
 static inline const DLevel &dl_of(const level_type *level) { return HPGMG_DEV(level)->L; }
+
+/* Every operator that writes vector `id` of a level through the public API says so: a diagonal that no longer
+ * comes from rebuild_operator_blackbox must be read from memory again, and recorded solves that baked the
+ * shortcut in are dropped (runtime.cu). */
+void hpgmg_dinv_overwritten(level_type *level);
+static inline void hpgmg_note_vector_written(level_type *level, const int id)
+{
+  if (id == VECTOR_DINV && HPGMG_DEV(level) && HPGMG_DEV(level)->dinv_is_unit_diagonal) hpgmg_dinv_overwritten(level);
+}
 
 /* max over non-negative doubles through their bit pattern (IEEE order == unsigned integer order) */
 __device__ __forceinline__ void atomic_max_nonneg(double *addr, double v)

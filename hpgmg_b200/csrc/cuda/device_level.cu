@@ -133,6 +133,7 @@ extern "C" void hpgmg_device_level_rebind_vectors(level_type *level)
 {
   hpgmg_device_level *D = HPGMG_DEV(level);
   DLevel &L = D->L;
+  if (L.base != NULL) hpgmg_graph_drop_all(NULL);     /* create_vectors moved the slab: recorded solves hold the old pointers */
   L.nboxes = level->num_my_boxes;
   L.nvec = level->numVectors;
   L.dim = level->box_dim;

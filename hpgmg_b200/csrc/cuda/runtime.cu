@@ -18,7 +18,13 @@ cudaStream_t g_stream = 0;
 unsigned long long g_launches = 0;
 int g_capturing = 0;
 int g_use_pdl = 1;
-extern "C" void hpgmg_b200_use_pdl(int on) { g_use_pdl = on ? 1 : 0; }
+extern "C" void hpgmg_b200_use_pdl(int on) { if ((on ? 1 : 0) != g_use_pdl) hpgmg_graph_drop_all(NULL); g_use_pdl = on ? 1 : 0; }
+
+void hpgmg_dinv_overwritten(level_type *level)
+{
+  HPGMG_DEV(level)->dinv_is_unit_diagonal = 0;
+  hpgmg_graph_drop_all(NULL);                       /* recorded sweeps formed 1/Aii in registers */
+}
 
 static int g_initialised = 0;
 static int g_device = -1;
@@ -202,7 +208,7 @@ extern "C" void hpgmg_upload_box_vector(level_type *level, int box, int id, cons
   const box_type *B = &level->my_boxes[box];
   hpgmg_rt_copy_h2d(B->vectors[id], host, (size_t)B->volume * sizeof(double));
   hpgmg_rt_sync();
-  if (id == VECTOR_DINV && HPGMG_DEV(level)) HPGMG_DEV(level)->dinv_is_unit_diagonal = 0;      /* a caller-supplied diagonal is read, not recomputed */
+  hpgmg_note_vector_written(level, id);               /* a caller-supplied diagonal is read, not recomputed */
 }
 
 /* ------------------------------------------------------------------------------------------ */
@@ -213,6 +219,7 @@ extern "C" void hpgmg_rt_zero_scalar(int slot)
 }
 extern "C" void hpgmg_rt_read_scalars(double *host, int first, int count)
 {
+  if (g_capturing) { fprintf(stderr, "hpgmg_b200: a host read-back (dot / norm / mean value) was requested inside a recorded solve; the caller must not capture this path\n"); abort(); }
   CUDA_CHECK(cudaMemcpyAsync(g_scalars_host + first, g_scalars + first, (size_t)count * sizeof(double), cudaMemcpyDeviceToHost, g_stream));
   CUDA_CHECK(cudaStreamSynchronize(g_stream));
   memcpy(host, g_scalars_host + first, (size_t)count * sizeof(double));
@@ -260,6 +267,7 @@ extern "C" void hpgmg_graph_end(const void *owner, long long key)
 
 extern "C" void hpgmg_graph_drop_all(const void *owner)
 {
+  if (g_capturing) { fprintf(stderr, "hpgmg_b200: the hierarchy was modified (vectors re-allocated / operator rebuilt / kernel switches) inside a recorded solve\n"); abort(); }
   for (size_t i = 0; i < g_graphs.size();) {
     if (owner == NULL || g_graphs[i].owner == owner) {
       cudaGraphExecDestroy(g_graphs[i].exec);

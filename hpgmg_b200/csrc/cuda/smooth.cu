@@ -27,7 +27,6 @@ struct StencilArgs {
                               stays clear of the boundary-condition ghost cells (the stored Dinv holds exactly that there) */
   int dom[3];              /* level dimensions in cells */
   double *norm_slot;       /* TMA residual kernel: also leave max |res| here (the norm the caller wants next), or NULL */
-  int l2hint;              /* TMA kernel: keep the face coefficients in L2 (evict_last); 2: and stream x (evict_first) */
 };
 
 /* generic one-thread-per-cell kernel (any box size) ------------------------------------------- */
@@ -83,80 +82,22 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(const StencilArgs 
   }
 }
 
-#include "stencil_tiled.cuh"
 #include "stencil_tma.cuh"
 #include <vector>
 
-static int g_tiled_async = 1, g_tma = 1, g_tma_blocks = 0, g_tma32 = 1, g_zigzag = 1, g_tma_chunks = 0, g_tma_cfg = 2, g_tma_cfg_full = 2, g_tma_cfg32 = 2, g_tma_minplanes = 8, g_diag = 1, g_l2hint = 0, g_l2hint_mb = 100, g_persistent_maxdim = 16;
-static int g_force_generic = -1, g_kchunk_override = -1, g_tile32 = 0, g_min_chunk = 16, g_persistent_smooth = 0, g_pair_kernel = 1;
+/* switches kept for A/B parity checks (tests/test_gpu_parity.py::test_kernel_variants_give_the_same_bits); read once */
+static int g_force_generic = -1, g_tma = 1, g_tma_blocks = 0, g_zigzag = 1, g_diag = 1, g_pair_kernel = 1, g_tma_minplanes = 8;
 
 static void stencil_env(void)
 {
-  if (g_force_generic < 0) {
-    const char *e = getenv("HPGMG_B200_GENERIC_STENCIL");
-    g_force_generic = (e && atoi(e)) ? 1 : 0;
-    const char *t32 = getenv("HPGMG_B200_TILE32");
-    if (t32) g_tile32 = atoi(t32);
-    const char *mc = getenv("HPGMG_B200_MIN_CHUNK");
-    if (mc) g_min_chunk = atoi(mc);
-    const char *pk = getenv("HPGMG_B200_PAIR_KERNEL");
-    if (pk) g_pair_kernel = atoi(pk);
-    const char *ps = getenv("HPGMG_B200_PERSISTENT_SMOOTH");
-    if (ps) g_persistent_smooth = atoi(ps);
-    const char *as = getenv("HPGMG_B200_TILED_ASYNC");
-    if (as) g_tiled_async = atoi(as);
-    const char *tm = getenv("HPGMG_B200_TMA");
-    if (tm) g_tma = atoi(tm);
-    const char *tb = getenv("HPGMG_B200_TMA_BLOCKS");
-    if (tb) g_tma_blocks = atoi(tb);
-    const char *zz = getenv("HPGMG_B200_ZIGZAG");
-    if (zz) g_zigzag = atoi(zz);
-    const char *tc = getenv("HPGMG_B200_TMA_CHUNKS");
-    if (tc) g_tma_chunks = atoi(tc);
-    const char *pm = getenv("HPGMG_B200_PERSISTENT_MAXDIM");
-    if (pm) g_persistent_maxdim = atoi(pm);
-    const char *lh = getenv("HPGMG_B200_L2HINT");
-    if (lh) g_l2hint = atoi(lh);
-    const char *lm = getenv("HPGMG_B200_L2HINT_MB");
-    if (lm) g_l2hint_mb = atoi(lm);
-    const char *dg = getenv("HPGMG_B200_DIAG");
-    if (dg) g_diag = atoi(dg);
-    const char *cf = getenv("HPGMG_B200_TMA_CFG");
-    if (cf) g_tma_cfg = g_tma_cfg_full = atoi(cf);
-    const char *c3 = getenv("HPGMG_B200_TMA_CFG32");         /* boxes of 32^3: one block per SM at most, so latency rules */
-    if (c3) g_tma_cfg32 = atoi(c3);
-    const char *mp = getenv("HPGMG_B200_TMA_MINPLANES");
-    if (mp) g_tma_minplanes = atoi(mp);
-    const char *cr = getenv("HPGMG_B200_TMA_CFG_FULL");      /* the operators that evaluate every cell: residual, Chebyshev, apply_op */
-    if (cr) g_tma_cfg_full = atoi(cr);
-    const char *t3 = getenv("HPGMG_B200_TMA32");
-    if (t3) g_tma32 = atoi(t3);
-    const char *kc = getenv("HPGMG_B200_KCHUNK");
-    if (kc) g_kchunk_override = atoi(kc);
-  }
-}
-
-template <int OP, int TI, int TJ>
-static void launch_tiled(const StencilArgs &A)
-{
-  typedef TileCfg<TI, TJ> C;
-  static bool configured = false;
-  if (!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(stencil_tiled_kernel<OP, TI, TJ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    CUDA_CHECK(cudaFuncSetAttribute(stencil_tiled_kernel<OP, TI, TJ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-    configured = true;
-  }
-  const int n = A.L.dim;
-  const int tiles = (n / TI) * (n / TJ);
-  /* split k so that the grid fills the 148 SMs x 2 resident blocks, but keep chunks >= 16 planes
-   * (each chunk re-reads a 4-plane prologue) */
-  int chunks = 1;
-  while (tiles * A.L.nboxes * chunks < 296 && n / (chunks * 2) >= g_min_chunk) chunks *= 2;
-  if (g_kchunk_override > 0) chunks = (n + g_kchunk_override - 1) / g_kchunk_override;
-  const int kchunk = (n + chunks - 1) / chunks;
-  dim3 grid(tiles, chunks, A.L.nboxes), block(TI / 2, TJ);
-  if (g_tiled_async) LAUNCH((stencil_tiled_kernel<OP, TI, TJ, true>), grid, block, C::SMEM, A, kchunk);
-  else               LAUNCH((stencil_tiled_kernel<OP, TI, TJ, false>), grid, block, C::SMEM, A, kchunk);
+  if (g_force_generic >= 0) return;
+  const char *e = getenv("HPGMG_B200_GENERIC_STENCIL");    /* every level through the one-thread-per-cell kernel */
+  g_force_generic = (e && atoi(e)) ? 1 : 0;
+  if ((e = getenv("HPGMG_B200_TMA")) != NULL) g_tma = atoi(e);                 /* 0: boxes >= 32^3 through the pair kernel */
+  if ((e = getenv("HPGMG_B200_TMA_BLOCKS")) != NULL) g_tma_blocks = atoi(e);   /* uneven split of the plane space */
+  if ((e = getenv("HPGMG_B200_ZIGZAG")) != NULL) g_zigzag = atoi(e);           /* 0: every sweep marches k upwards */
+  if ((e = getenv("HPGMG_B200_DIAG")) != NULL) g_diag = atoi(e);               /* 0: Dinv always read from memory */
+  if ((e = getenv("HPGMG_B200_PAIR_KERNEL")) != NULL) g_pair_kernel = atoi(e); /* 0: small boxes through the generic kernel */
 }
 
 /* ---- TMA descriptors: the level slab [box*vector][k][j][i] as a rank-4 tensor, one (W x rows) tile per copy ---- */
@@ -228,30 +169,11 @@ static void launch_tma(const StencilArgs &A)
   long long chunks = slots / columns;
   if (chunks > n / g_tma_minplanes) chunks = n / g_tma_minplanes;
   if (chunks < 1) chunks = 1;
-  if (g_tma_chunks > 0) chunks = g_tma_chunks;
   while (n % chunks) chunks--;
   long long blocks = g_tma_blocks > 0 ? g_tma_blocks : columns * chunks;
   if (OP == OP_RESIDUAL && A.norm_slot) g_norm_fused = true;
   if (A.reverse && OP == OP_GSRB) LAUNCH((stencil_tma_kernel<OP, TI, TJ, PF, MINB, (OP == OP_GSRB)>), dim3((unsigned)blocks), dim3(C::NT), C::SMEM, A, M->x, M->b, total);
   else                            LAUNCH((stencil_tma_kernel<OP, TI, TJ, PF, MINB, false>), dim3((unsigned)blocks), dim3(C::NT), C::SMEM, A, M->x, M->b, total);
-}
-
-/* tile shape / prefetch depth / residency of the TMA kernel (HPGMG_B200_TMA_CFG, for experiments) */
-template <int OP>
-static bool launch_tma_cfg(const StencilArgs &A, const int cfg)
-{
-  const int n = A.L.dim;
-  switch (cfg) {
-    case 0: if (n % 64) return false; launch_tma<OP, 64, 8, 1, 2>(A); return true;
-    case 1: if (n % 64) return false; launch_tma<OP, 64, 16, 2, 1>(A); return true;
-    case 2: if (n % 32) return false; launch_tma<OP, 32, 8, 1, 4>(A); return true;
-    case 3: if (n % 32) return false; launch_tma<OP, 32, 16, 2, 2>(A); return true;
-    case 4: if (n % 32) return false; launch_tma<OP, 32, 8, 2, 3>(A); return true;
-    case 5: if (n % 32) return false; launch_tma<OP, 32, 16, 1, 2>(A); return true;
-    case 6: if (n % 64) return false; launch_tma<OP, 64, 16, 1, 1>(A); return true;
-    case 7: if (n % 32) return false; launch_tma<OP, 32, 8, 3, 2>(A); return true;
-    default: return false;
-  }
 }
 
 /* Small even boxes (<= 32^3): one thread per i-PAIR of cells, straight from global memory through L1.
@@ -307,10 +229,6 @@ static void launch_stencil(level_type *level, StencilArgs &A)
   A.low = HPGMG_DEV(level)->low;
   A.h2inv = 1.0 / (level->h * level->h);
   A.dom[0] = level->dim.i;  A.dom[1] = level->dim.j;  A.dom[2] = level->dim.k;
-  {                         /* operator data (3 betas + rhs) of the boxes on this GPU small enough to live in L2 across sweeps? */
-    const double mb = 4.0 * (double)L.nboxes * (double)L.volume * 8.0 / 1e6;
-    A.l2hint = (g_l2hint && mb <= (double)g_l2hint_mb) ? g_l2hint : 0;
-  }
   /* the identity behind `diag` needs the 4^3-colour black-box diagonal (rebuild_operator, operators.fv4.c:145-173:
    * no two cells of a colour within one stencil) and Dirichlet ghost cells that only cells within 2 of the
    * boundary can see */
@@ -319,10 +237,7 @@ static void launch_stencil(level_type *level, StencilArgs &A)
   stencil_env();
   if (OP != OP_REBUILD && hpgmg_ablate(n < 64 ? 8 : (OP == OP_RESIDUAL ? 32 : 64))) return;
   if (OP != OP_REBUILD && !g_force_generic) {
-    if (n % 32 == 0 && n >= 64 && (g_tile32 == 2 || (g_tile32 == 1 && n == 64))) { launch_tiled<OP, 32, 8>(A); return; }
-    if (n >= 64 && g_tma && launch_tma_cfg<OP>(A, OP == OP_GSRB ? g_tma_cfg : g_tma_cfg_full)) return;
-    if (n == 32 && g_tma32 && launch_tma_cfg<OP>(A, g_tma_cfg32)) return;
-    if (n % 64 == 0) { launch_tiled<OP, 64, 8>(A); return; }
+    if (n % 32 == 0 && g_tma) { launch_tma<OP, 32, 8, 1, 4>(A); return; }       /* boxes of 32^3 .. 256^3 */
     if ((n & 1) == 0 && n >= 4 && g_pair_kernel) {
       const int hn = n / 2;
       dim3 block(hn >= 16 ? 16 : hn, n >= 8 ? 8 : n, hn >= 16 ? 2 : (n >= 8 ? 256 / (hn * 8) : 256 / (hn * n)));
@@ -352,6 +267,7 @@ extern "C" int stencil_get_shape(void) { return STENCIL_SHAPE_NO_CORNERS; }
 extern "C" void apply_op(level_type *level, int Ax_id, int x_id, double a, double b)
 {
   ProfileScope prof_(&level->timers.apply_op);
+  hpgmg_note_vector_written(level, Ax_id);
   fill_ghosts(level, x_id);
   StencilArgs A = {};
   A.x_id = x_id;  A.out_id = Ax_id;  A.a = a;  A.b = b;
@@ -361,6 +277,7 @@ extern "C" void apply_op(level_type *level, int Ax_id, int x_id, double a, doubl
 extern "C" void residual(level_type *level, int res_id, int x_id, int rhs_id, double a, double b)
 {
   ProfileScope prof_(&level->timers.residual);
+  hpgmg_note_vector_written(level, res_id);
   fill_ghosts(level, x_id);
   StencilArgs A = {};
   A.x_id = x_id;  A.rhs_id = rhs_id;  A.out_id = res_id;  A.a = a;  A.b = b;
@@ -406,129 +323,6 @@ extern "C" void hpgmg_b200_gsrb_sweep(level_type *level, int src_id, int dst_id,
   launch_stencil<OP_GSRB>(level, A);
 }
 
-/* ---- small levels: a whole smooth() as ONE persistent kernel ---------------------------------------- */
-/* EXPERIMENT, off by default (HPGMG_B200_PERSISTENT_SMOOTH=1): measured 8.34 ms vs 8.15 ms per `7 8` solve --
- * inside a CUDA graph the 12 launches it replaces are cheaper than its 11 grid barriers at 8 warps/SM.
- * Boxes of <= 32^3 cells that live entirely on this GPU: the 6 x (ghost fill, sweep) of a smooth are
- * microsecond-sized.  One cooperative kernel (all blocks co-resident) runs the 12 phases back to back,
- * separated by a grid-wide barrier; a thread owns an
- * i-pair of cells, so on a red-black sweep every lane evaluates exactly one stencil.  Same device
- * bodies as the stand-alone kernels (fill.cuh, stencil.cuh): same bits. */
-#include "fill.cuh"
-
-struct SmoothArgs {
-  DLevel L;
-  const int *low;
-  const FillCopy *copies;  int ncopies;
-  const FillBC *bc;        int nbc;
-  int x_id, rhs_id, version, cheby;
-  double b, h2inv;
-  double c1[6], c2[6];
-  unsigned int *barrier;                           /* zeroed before the launch */
-};
-
-__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int &generation)
-{
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    generation++;
-    atomicAdd(bar, 1u);
-    while (*(volatile unsigned int *)bar < generation * gridDim.x) { }
-    __threadfence();
-  }
-  __syncthreads();
-}
-
-/* CLUSTER: the grid is one thread-block cluster and the phases are separated by the hardware cluster barrier
- * (boxes <= 16^3: a few thousand pairs, 8 or 16 blocks); otherwise a cooperative grid with a software barrier. */
-template <bool CLUSTER>
-__global__ void __launch_bounds__(256, 1) smooth_persistent_kernel(const SmoothArgs A)
-{
-  PDL_WAIT();
-  const DLevel &L = A.L;
-  const int n = L.dim, hn = n / 2, jS = L.jStride, kS = L.kStride;
-  const int gthreads = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int pairs_per_box = hn * n * n, pairs = pairs_per_box * L.nboxes;
-  unsigned int generation = 0;
-  for (int s = 0; s < 6; s++) {
-    const int src = (s & 1) ? VECTOR_TEMP : A.x_id, dst = (s & 1) ? A.x_id : VECTOR_TEMP;
-    for (int t = gtid; t < A.ncopies + A.nbc; t += gthreads) fill_items(L, src, t, A.copies, A.ncopies, A.bc, A.nbc, A.version);
-    if (CLUSTER) cluster_barrier(); else grid_barrier(A.barrier, generation);
-    for (int q = gtid; q < pairs; q += gthreads) {
-      const int box = q / pairs_per_box, c = q - box * pairs_per_box;
-      const int p = c % hn, j = (c / hn) % n, k = c / (hn * n);
-      const int ijk = 2 * p + j * jS + k * kS;
-      const double *x = L.vec(box, src) + ijk;
-      const double *bi = L.vec(box, VECTOR_BETA_I) + ijk, *bj = L.vec(box, VECTOR_BETA_J) + ijk, *bk = L.vec(box, VECTOR_BETA_K) + ijk;
-      const double2 rhs2 = *reinterpret_cast<const double2 *>(L.vec(box, A.rhs_id) + ijk);
-      const double2 dinv2 = *reinterpret_cast<const double2 *>(L.vec(box, VECTOR_DINV) + ijk);
-      double2 *out = reinterpret_cast<double2 *>(L.vec(box, dst) + ijk);
-      if (!A.cheby) {
-        const int color000 = (A.low[3 * box] ^ A.low[3 * box + 1] ^ A.low[3 * box + 2] ^ s) & 1;
-        const int a = (j ^ k ^ color000) & 1;                 /* the active cell of the pair */
-        const double Ax = fv4_apply_op(x + a, bi + a, bj + a, bk + a, jS, kS, A.b, A.h2inv);
-        const double xnew = x[a] + (a ? dinv2.y : dinv2.x) * ((a ? rhs2.y : rhs2.x) - Ax);
-        const double xo = x[1 - a];
-        *out = a ? make_double2(xo, xnew) : make_double2(xnew, xo);
-      } else {
-        const double2 xm = *out;                               /* x_nm1 aliases x_np1 (chebyshev.c:75-80) */
-        const double Ax0 = fv4_apply_op(x, bi, bj, bk, jS, kS, A.b, A.h2inv);
-        const double Ax1 = fv4_apply_op(x + 1, bi + 1, bj + 1, bk + 1, jS, kS, A.b, A.h2inv);
-        const double r0 = x[0] + A.c1[s] * (x[0] - xm.x) + A.c2[s] * dinv2.x * (rhs2.x - Ax0);
-        const double r1 = x[1] + A.c1[s] * (x[1] - xm.y) + A.c2[s] * dinv2.y * (rhs2.y - Ax1);
-        *out = make_double2(r0, r1);
-      }
-    }
-    if (s < 5) { if (CLUSTER) cluster_barrier(); else grid_barrier(A.barrier, generation); }
-  }
-}
-
-static unsigned int *g_smooth_barrier = NULL;
-
-/* 1 if the smooth was enqueued as the persistent kernel */
-static int smooth_persistent(level_type *level, int x_id, int rhs_id, double a, double b)
-{
-  hpgmg_device_level *D = HPGMG_DEV(level);
-  const DLevel &L = D->L;
-  stencil_env();
-  if (!g_persistent_smooth || L.nboxes == 0 || (L.dim & 1) || L.dim > (g_persistent_smooth == 1 ? 32 : g_persistent_maxdim) || L.dim < 4) return 0;
-  if (level->boundary_condition.type != BC_DIRICHLET || level->box_ghosts != 2 || D->fill_nvec != level->numVectors) return 0;
-  const communicator_type *C = &level->exchange_ghosts[STENCIL_SHAPE_NO_CORNERS];
-  if (C->num_sends > 0 || C->num_recvs > 0) return 0;                       /* neighbours on other GPUs: the kernel-per-phase path */
-  if (!g_smooth_barrier) g_smooth_barrier = reinterpret_cast<unsigned int *>(hpgmg_rt_scalar_slots() + HPGMG_SLOT_BARRIER);   /* preallocated: no cudaMalloc during capture */
-  const FillTable &T = D->fill[STENCIL_SHAPE_NO_CORNERS];
-  SmoothArgs A;
-  memset(&A, 0, sizeof(A));
-  A.L = L;  A.low = D->low;
-  A.copies = T.copies;  A.ncopies = T.ncopies;  A.bc = T.bc;  A.nbc = T.nbc;
-  A.x_id = x_id;  A.rhs_id = rhs_id;  A.version = 4;  A.b = b;  A.h2inv = 1.0 / (level->h * level->h);
-  A.cheby = hpgmg_rt_smoother() == HPGMG_SMOOTHER_CHEBY;
-  if (A.cheby) {                                                            /* chebyshev.c:22-40 */
-    double beta = 1.000 * level->dominant_eigenvalue_of_DinvA, alpha = 0.125000 * beta;
-    double theta = 0.5 * (beta + alpha), delta = 0.5 * (beta - alpha), sigma = theta / delta, rho_n = 1 / sigma;
-    A.c1[0] = 0.0;  A.c2[0] = 1 / theta;
-    for (int s = 1; s < 6; s++) { double rho_nm1 = rho_n; rho_n = 1.0 / (2.0 * sigma - rho_nm1); A.c1[s] = rho_n * rho_nm1; A.c2[s] = rho_n * 2.0 / delta; }
-  }
-  A.barrier = g_smooth_barrier;
-  const int pairs = (L.dim / 2) * L.dim * L.dim * L.nboxes;
-  int blocks = (pairs + 255) / 256;
-  if (g_persistent_smooth >= 2) {                                           /* one cluster, hardware barrier */
-    const int cmax = g_persistent_smooth >= 16 ? 16 : 8;
-    if (blocks > cmax) blocks = cmax;
-    static bool configured = false;
-    if (!configured) { CUDA_CHECK(cudaFuncSetAttribute(smooth_persistent_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)); configured = true; }
-    hpgmg_launch_cluster("smooth_persistent_kernel<cluster>", smooth_persistent_kernel<true>, dim3(blocks), dim3(256), 0, A);
-    (void)a;
-    return 1;
-  }
-  if (blocks > 148) blocks = 148;                                           /* one block per SM: all co-resident */
-  CUDA_CHECK(cudaMemsetAsync(g_smooth_barrier, 0, sizeof(unsigned int), g_stream));
-  hpgmg_launch_cooperative("smooth_persistent_kernel", smooth_persistent_kernel<false>, dim3(blocks), dim3(256), 0, A);
-  (void)a;
-  return 1;
-}
-
 static void smooth_chebyshev(level_type *level, int x_id, int rhs_id, double a, double b)
 {
   enum { DEGREE = 6 };                               /* CHEBYSHEV_DEGREE (operators.fv4.c:184) */
@@ -563,7 +357,7 @@ static void smooth_chebyshev(level_type *level, int x_id, int rhs_id, double a, 
 extern "C" void smooth(level_type *level, int x_id, int rhs_id, double a, double b)
 {
   ProfileScope prof_(&level->timers.smooth);
-  if (smooth_persistent(level, x_id, rhs_id, a, b)) return;
+  hpgmg_note_vector_written(level, x_id);
   if (hpgmg_rt_smoother() == HPGMG_SMOOTHER_CHEBY) smooth_chebyshev(level, x_id, rhs_id, a, b);
   else smooth_gsrb(level, x_id, rhs_id, a, b);
 }
@@ -634,6 +428,7 @@ extern "C" void rebuild_operator_blackbox(level_type *level, double a, double b,
   if (chatty && hpgmg_rt_smoother() == HPGMG_SMOOTHER_CHEBY) { fprintf(stdout, "  estimating  lambda_max... <%1.15e\n", eig); fflush(stdout); }
   level->dominant_eigenvalue_of_DinvA = eig;
   HPGMG_DEV(level)->dinv_is_unit_diagonal = (colors_in_each_dim >= 4) ? 1 : 0;
+  hpgmg_graph_drop_all(NULL);                          /* recorded solves carry the old eigenvalue / diagonal shortcut by value */
 }
 
 extern "C" void rebuild_operator(level_type *level, level_type *fromLevel, double a, double b)

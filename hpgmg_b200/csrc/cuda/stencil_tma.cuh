@@ -2,10 +2,9 @@
  * stencil_tma.cuh -- the operator kernels for boxes >= 32^3, Blackwell version: 2.5-D blocking with the halo
  * tiles staged in shared memory by the TMA engine.
  *
- * What it computes is what stencil_tiled.cuh computes (GSRB / Chebyshev / residual / apply_op on a
- * TI x TJ column of cells marching along k; gsrb.c:41-129, chebyshev.c:51-97, residual.c:18-49,
- * apply_op.c:18-47 with the macro of operators.fv4.c:87-114) -- the arithmetic is the same
- * fv4_apply_op_at, hence the same bits.  What changed is everything around the arithmetic:
+ * GSRB / Chebyshev / residual / apply_op on a TI x TJ column of cells marching along k (gsrb.c:41-129,
+ * chebyshev.c:51-97, residual.c:18-49, apply_op.c:18-47 with the macro of operators.fv4.c:87-114); the
+ * arithmetic is fv4_apply_op_at, shared with every other kernel, hence the same bits.  Around the arithmetic:
  *
  *  - staging: one elected thread issues cp.async.bulk.tensor (TMA) copies of whole (TI+4) x rows tiles
  *    of x, beta_i, beta_j, beta_k PF steps ahead into ring buffers; completion is counted by mbarriers
@@ -81,28 +80,6 @@ __device__ __forceinline__ void tma_load_4d(const unsigned dst, const CUtensorMa
                ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
 
-/* the same with an L2 eviction-priority hint (createpolicy): the face coefficients of a level whose operator data
- * fits in the 126 MB L2 are kept there across the sweeps of a smooth (evict_last) while x streams through */
-__device__ __forceinline__ void tma_load_4d_hint(const unsigned dst, const CUtensorMap *map, const int c0, const int c1, const int c2, const int c3, const unsigned bar, const unsigned long long policy)
-{
-  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;"
-               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar), "l"(policy) : "memory");
-}
-__device__ __forceinline__ unsigned long long l2_policy_evict_last()
-{
-  unsigned long long p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ unsigned long long l2_policy_evict_first()
-{
-  unsigned long long p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-#define TMA_LOAD_B(dst, map, c0, c1, c2, c3, bar) do { if (keep_b) tma_load_4d_hint(dst, map, c0, c1, c2, c3, bar, pol_b); else tma_load_4d(dst, map, c0, c1, c2, c3, bar); } while (0)
-#define TMA_LOAD_X(dst, map, c0, c1, c2, c3, bar) do { if (stream_x) tma_load_4d_hint(dst, map, c0, c1, c2, c3, bar, pol_x); else tma_load_4d(dst, map, c0, c1, c2, c3, bar); } while (0)
-
 /* shared-memory loader: a[d] is the byte address of the lane's active cell in the ring slot that holds
  * plane k + DK0 + d; an operand at (di,dj,dk) is a load at a compile-time offset from it. */
 template <int W, int DK0, int NPLANES>
@@ -138,9 +115,6 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
   const DLevel &L = A.L;
   const int n = L.dim, jS = L.jStride, kS = L.kStride;
   const int tiles_i = n / TI, tiles = tiles_i * (n / TJ);
-  const bool keep_b = A.l2hint != 0;
-  const bool stream_x = A.l2hint == 2;
-  const unsigned long long pol_b = l2_policy_evict_last(), pol_x = l2_policy_evict_first();
 
   /* lane -> (row, pair): even lanes row 2rp, odd lanes row 2rp+1; 16 consecutive pairs per warp */
   constexpr int WPR = (TI / 2) / 16;                                /* warps per row pair */
@@ -175,23 +149,23 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
     if (tid == 0) {
       mbar_expect_tx(bar0, 5 * C::XBYTES + 8 * C::BBYTES);
 #pragma unroll
-      for (int d = 0; d < 5; d++) TMA_LOAD_X(xs + d * C::XPB, &map_x, ci, cjx, kf + (d - 2) * dir + g, cx, bar0);
+      for (int d = 0; d < 5; d++) tma_load_4d(xs + d * C::XPB, &map_x, ci, cjx, kf + (d - 2) * dir + g, cx, bar0);
 #pragma unroll
       for (int d = 0; d < 3; d++) {
-        TMA_LOAD_B(bis + d * C::BPB, &map_b, ci, cjb, kf + (d - 1) * dir + g, cbi, bar0);
-        TMA_LOAD_B(bjs + d * C::BPB, &map_b, ci, cjb, kf + (d - 1) * dir + g, cbj, bar0);
+        tma_load_4d(bis + d * C::BPB, &map_b, ci, cjb, kf + (d - 1) * dir + g, cbi, bar0);
+        tma_load_4d(bjs + d * C::BPB, &map_b, ci, cjb, kf + (d - 1) * dir + g, cbj, bar0);
       }
 #pragma unroll
-      for (int d = 0; d < 2; d++) TMA_LOAD_B(bks + d * C::BPB, &map_b, ci, cjb, kf + (REV ? 1 - d : d) + g, cbk, bar0);
+      for (int d = 0; d < 2; d++) tma_load_4d(bks + d * C::BPB, &map_b, ci, cjb, kf + (REV ? 1 - d : d) + g, cbk, bar0);
 #pragma unroll
       for (int q = 1; q < PF; q++)
         if (q < len) {
           const unsigned bq = bar0 + 8 * (q % C::NB);
           mbar_expect_tx(bq, C::XBYTES + 3 * C::BBYTES);
-          TMA_LOAD_X(xs + ((q + 4) % C::XP) * C::XPB, &map_x, ci, cjx, kf + (q + 2) * dir + g, cx, bq);
-          TMA_LOAD_B(bis + ((q + 2) % C::BP) * C::BPB, &map_b, ci, cjb, kf + (q + 1) * dir + g, cbi, bq);
-          TMA_LOAD_B(bjs + ((q + 2) % C::BP) * C::BPB, &map_b, ci, cjb, kf + (q + 1) * dir + g, cbj, bq);
-          TMA_LOAD_B(bks + ((q + 1) % C::KP) * C::BPB, &map_b, ci, cjb, kf + (REV ? -q : q + 1) + g, cbk, bq);
+          tma_load_4d(xs + ((q + 4) % C::XP) * C::XPB, &map_x, ci, cjx, kf + (q + 2) * dir + g, cx, bq);
+          tma_load_4d(bis + ((q + 2) % C::BP) * C::BPB, &map_b, ci, cjb, kf + (q + 1) * dir + g, cbi, bq);
+          tma_load_4d(bjs + ((q + 2) % C::BP) * C::BPB, &map_b, ci, cjb, kf + (q + 1) * dir + g, cbj, bq);
+          tma_load_4d(bks + ((q + 1) % C::KP) * C::BPB, &map_b, ci, cjb, kf + (REV ? -q : q + 1) + g, cbk, bq);
         }
     }
 
@@ -241,10 +215,10 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
         const int qn = bq == 0 ? C::NB - 1 : bq - 1;                 /* (t + PF) mod NB == (t - 1) mod NB */
         const unsigned bn = bar0 + 8 * qn;
         mbar_expect_tx(bn, C::XBYTES + 3 * C::BBYTES);
-        TMA_LOAD_X(xs + nx * C::XPB, &map_x, ci, cjx, k + (PF + 2) * dir + g, cx, bn);
-        TMA_LOAD_B(bis + nb * C::BPB, &map_b, ci, cjb, k + (PF + 1) * dir + g, cbi, bn);
-        TMA_LOAD_B(bjs + nb * C::BPB, &map_b, ci, cjb, k + (PF + 1) * dir + g, cbj, bn);
-        TMA_LOAD_B(bks + nk * C::BPB, &map_b, ci, cjb, k + (REV ? -PF : PF + 1) + g, cbk, bn);
+        tma_load_4d(xs + nx * C::XPB, &map_x, ci, cjx, k + (PF + 2) * dir + g, cx, bn);
+        tma_load_4d(bis + nb * C::BPB, &map_b, ci, cjb, k + (PF + 1) * dir + g, cbi, bn);
+        tma_load_4d(bjs + nb * C::BPB, &map_b, ci, cjb, k + (PF + 1) * dir + g, cbj, bn);
+        tma_load_4d(bks + nk * C::BPB, &map_b, ci, cjb, k + (REV ? -PF : PF + 1) + g, cbk, bn);
       }
       const double2 rhs2 = rhs_n, dinv2 = dinv_n, xm2 = xm_n;
       if (more) {

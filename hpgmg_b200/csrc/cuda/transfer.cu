@@ -87,6 +87,7 @@ extern "C" void restriction(level_type *level_c, int id_c, level_type *level_f, 
 {
   ProfileScope prof_(&level_f->timers.restriction_total);
   if (hpgmg_ablate(16)) return;
+  hpgmg_note_vector_written(level_c, id_c);
   hpgmg_device_level *Df = HPGMG_DEV(level_f), *Dc = HPGMG_DEV(level_c);
   communicator_type *Cf = &level_f->restriction[restrictionType], *Cc = &level_c->restriction[restrictionType];
   const int remote = (Cf->num_sends > 0) || (Cc->num_recvs > 0);
@@ -347,6 +348,7 @@ static void interpolation_driver(level_type *level_f, int id_f, double prescale_
 {
   ProfileScope prof_(&level_f->timers.interpolation_total);
   if (hpgmg_ablate(16)) return;
+  hpgmg_note_vector_written(level_f, id_f);
   hpgmg_device_level *Df = HPGMG_DEV(level_f), *Dc = HPGMG_DEV(level_c);
   communicator_type *Cc = &level_c->interpolation, *Cf = &level_f->interpolation;
   const int remote = (Cc->num_sends > 0) || (Cf->num_recvs > 0);

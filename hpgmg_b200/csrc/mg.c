@@ -432,11 +432,13 @@ void MGBuild(mg_type *MG, level_type *fine, double a, double b, int minCoarseGri
 }
 
 /* ------------------------------------------------------------------------------------------ */
+static void hpgmg_forget_norms(const mg_type *MG);
 void MGDestroy(mg_type *MG)
 {
   const int chatty = (MG->my_rank == 0) && hpgmg_rt_verbose();
   hpgmg_rt_sync();
   hpgmg_graph_drop_all(MG);
+  hpgmg_forget_norms(MG);
   if (chatty) { fprintf(stdout, "attempting to free the restriction and interpolation lists... "); fflush(stdout); }
   for (int l = MG->num_levels - 1; l >= 0; l--) {
     hpgmg_free_communicator(&MG->levels[l]->interpolation);
@@ -510,11 +512,53 @@ void MGVCycle(mg_type *MG, int e_id, int R_id, double a, double b, int level)
 
 /* ------------------------------------------------------------------------------------------ */
 /* bookkeeping shared by the solve drivers */
-typedef struct { double norm_of_F, norm_of_residual; } solve_norms;
-static solve_norms g_last = { 0.0, 0.0 };
-static const mg_type *g_last_owner = NULL;
-double hpgmg_last_norm_of_F(const mg_type *MG)        { (void)MG; return g_last.norm_of_F; }
-double hpgmg_last_norm_of_residual(const mg_type *MG) { (void)MG; return g_last.norm_of_residual; }
+/* ||F|| and ||r|| of the last solve, kept per hierarchy (the reference only prints them, mg.c:1325-1329) */
+typedef struct { const mg_type *owner; double norm_of_F, norm_of_residual; } solve_norms;
+#define MAX_TRACKED_HIERARCHIES 16
+static solve_norms g_last[MAX_TRACKED_HIERARCHIES];
+static int g_last_next = 0;
+static solve_norms *last_norms_of(const mg_type *MG, int create)
+{
+  for (int i = 0; i < MAX_TRACKED_HIERARCHIES; i++) if (g_last[i].owner == MG) return &g_last[i];
+  if (!create) return NULL;
+  solve_norms *s = &g_last[g_last_next];              /* round robin: the oldest hierarchy's record is recycled */
+  g_last_next = (g_last_next + 1) % MAX_TRACKED_HIERARCHIES;
+  s->owner = MG;  s->norm_of_F = s->norm_of_residual = 0.0;
+  return s;
+}
+static void record_norms(const mg_type *MG, double norm_of_F, double norm_of_residual)
+{
+  solve_norms *s = last_norms_of(MG, 1);
+  s->norm_of_F = norm_of_F;  s->norm_of_residual = norm_of_residual;
+}
+double hpgmg_last_norm_of_F(const mg_type *MG)        { const solve_norms *s = last_norms_of(MG, 0); return s ? s->norm_of_F : 0.0; }
+double hpgmg_last_norm_of_residual(const mg_type *MG) { const solve_norms *s = last_norms_of(MG, 0); return s ? s->norm_of_residual : 0.0; }
+
+/* Can a whole solve on this hierarchy be recorded into a CUDA graph?  Only if nothing in it needs a host
+ * read-back: no mean subtraction (periodic), no per-operator timers, and a bottom solve that runs as one
+ * device kernel (single-block coarse cycle or single-block BiCGStab) -- the host-driven BiCGStab of
+ * solvers.c synchronises on every dot / norm. */
+int hpgmg_bicgstab_device_eligible(const level_type *level);      /* bicgstab.cu */
+static int solve_is_capturable(mg_type *MG, const level_type *L)
+{
+  if (!hpgmg_rt_use_graphs() || hpgmg_rt_profile() || L->must_subtract_mean == 1) return 0;
+  const int bottom = MG->num_levels - 1;
+  const level_type *B = MG->levels[bottom];
+  if (!B->active) return 1;                            /* this rank never touches the bottom level */
+  return hpgmg_coarse_chain_eligible(MG, bottom) || hpgmg_bicgstab_device_eligible(B);
+}
+
+/* the bottom solver counts its iterations on the device (HPGMG_SLOT_KRYLOV); every driver zeroes the slot
+ * before enqueueing cycles and adds it to the bottom level's counter when it next synchronises */
+static void hpgmg_forget_norms(const mg_type *MG) { solve_norms *s = last_norms_of(MG, 0); if (s) s->owner = NULL; }
+static void krylov_count_begin(void) { hpgmg_rt_zero_scalar(HPGMG_SLOT_KRYLOV); }
+static void krylov_count_collect(mg_type *MG)
+{
+  double its = 0.0;
+  hpgmg_rt_read_scalars(&its, HPGMG_SLOT_KRYLOV, 1);
+  MG->levels[MG->num_levels - 1]->Krylov_iterations += (int)its;
+  hpgmg_rt_zero_scalar(HPGMG_SLOT_KRYLOV);
+}
 
 static int g_fmg_post_vcycles = 0;     /* the reference's -DUNLIMIT_FMG_ITERATIONS => 20 (mg.c:1243-1247) */
 void hpgmg_b200_set_fmg_post_vcycles(int n) { g_fmg_post_vcycles = n; }
@@ -585,7 +629,7 @@ void FMGSolve(mg_type *MG, int onLevel, int u_id, int F_id, double a, double b, 
   if (chatty) fprintf(stdout, "FMGSolve... ");
   const double t0 = hpgmg_rt_wtime();
 
-  const int capturable = hpgmg_rt_use_graphs() && !hpgmg_rt_profile() && (L->must_subtract_mean != 1);
+  const int capturable = solve_is_capturable(MG, L);
   const long long key = solve_key(1, onLevel, u_id, F_id, a, b);
   hpgmg_rt_timer_start();
   if (!capturable || hpgmg_graph_begin(MG, key)) {
@@ -608,16 +652,18 @@ void FMGSolve(mg_type *MG, int onLevel, int u_id, int F_id, double a, double b, 
     L->vcycles_from_this_level++;
     const long long vkey = solve_key(2, onLevel, u_id, F_id, a, b);
     if (!capturable || hpgmg_graph_begin(MG, vkey)) {
+      hpgmg_rt_zero_scalar(HPGMG_SLOT_KRYLOV);
       MGVCycle(MG, e_id, R_id, a, b, onLevel);
       enqueue_residual_norm(L, e_id, F_id, a, b);
       if (capturable) hpgmg_graph_end(MG, vkey);
     }
-    hpgmg_rt_read_scalars(s, HPGMG_SLOT_NORM_R, 1);
+    hpgmg_rt_read_scalars(s, HPGMG_SLOT_NORM_R, 2);
     norm_of_residual = s[0];
+    MG->levels[MG->num_levels - 1]->Krylov_iterations += (int)s[1];
     if (chatty) fprintf(stdout, "\n            v-cycle=%2d  norm=%1.15e  rel=%1.15e  ", v + 1, norm_of_residual, norm_of_residual / norm_of_F);
   }
 
-  g_last.norm_of_F = norm_of_F;  g_last.norm_of_residual = norm_of_residual;  g_last_owner = MG;
+  record_norms(MG, norm_of_F, norm_of_residual);
   const double dt = hpgmg_rt_wtime() - t0;
   MG->timers.MGSolve += dt;
   if (chatty) fprintf(stdout, "done (%f seconds)\n", dt);
@@ -634,28 +680,30 @@ void MGSolve(mg_type *MG, int onLevel, int u_id, int F_id, double a, double b, d
   const int chatty = (L->my_rank == 0) && hpgmg_rt_verbose();
   if (chatty) fprintf(stdout, "MGSolve... ");
   const double t0 = hpgmg_rt_wtime();
-  const int capturable = hpgmg_rt_use_graphs() && !hpgmg_rt_profile() && (L->must_subtract_mean != 1);
+  const int capturable = solve_is_capturable(MG, L);
 
   hpgmg_rt_timer_start();
   hpgmg_norm_async(L, F_id, HPGMG_SLOT_NORM_F);
   zero_vector(L, e_id);
   scale_vector(L, R_id, 1.0, F_id);
-  double s[2] = { 1.0, 0.0 };
+  double s[3] = { 1.0, 0.0, 0.0 };
   for (int v = 0; v < maxVCycles; v++) {
     L->vcycles_from_this_level++;
     const long long key = solve_key(3, onLevel, u_id, F_id, a, b);
     if (!capturable || hpgmg_graph_begin(MG, key)) {
+      hpgmg_rt_zero_scalar(HPGMG_SLOT_KRYLOV);
       MGVCycle(MG, e_id, R_id, a, b, onLevel);
       enqueue_residual_norm(L, e_id, F_id, a, b);
       if (capturable) hpgmg_graph_end(MG, key);
     }
-    hpgmg_rt_read_scalars(s, HPGMG_SLOT_NORM_F, 2);
+    hpgmg_rt_read_scalars(s, HPGMG_SLOT_NORM_F, 3);
+    MG->levels[MG->num_levels - 1]->Krylov_iterations += (int)s[2];
     if (chatty) fprintf(stdout, v > 0 ? "\n           v-cycle=%2d  norm=%1.15e  rel=%1.15e  " : "v-cycle=%2d  norm=%1.15e  rel=%1.15e  ",
                         v + 1, s[1], s[1] / s[0]);
     if (s[1] / s[0] < rtol) break;
   }
   hpgmg_rt_timer_stop();
-  g_last.norm_of_F = s[0];  g_last.norm_of_residual = s[1];  g_last_owner = MG;
+  record_norms(MG, s[0], s[1]);
   const double dt = hpgmg_rt_wtime() - t0;
   MG->timers.MGSolve += dt;
   if (chatty) fprintf(stdout, "done (%f seconds)\n", dt);
@@ -676,6 +724,7 @@ void FMGSolve2(mg_type *MG, int onLevel, int u_id, int F_id, double a, double b,
   const double t0 = hpgmg_rt_wtime();
 
   hpgmg_rt_timer_start();
+  krylov_count_begin();
   residual(L, R_id, u_id, F_id, a, b);
   double norm_of_residual = norm(L, R_id);
   double norm_of_F = norm(L, F_id);
@@ -700,11 +749,12 @@ void FMGSolve2(mg_type *MG, int onLevel, int u_id, int F_id, double a, double b,
     }
     residual(L, R_id, u_id, F_id, a, b);
     norm_of_residual = norm(L, R_id);
+    krylov_count_collect(MG);
     if (chatty) fprintf(stdout, "            f-cycle=%2d  norm=%1.15e  rel=%1.15e\n", f + 1, norm_of_residual, norm_of_residual / norm_of_F);
     if (norm_of_residual / norm_of_F < rtol) break;
   }
   hpgmg_rt_timer_stop();
-  g_last.norm_of_F = norm_of_F;  g_last.norm_of_residual = norm_of_residual;  g_last_owner = MG;
+  record_norms(MG, norm_of_F, norm_of_residual);
   const double dt = hpgmg_rt_wtime() - t0;
   MG->timers.MGSolve += dt;
   if (chatty) fprintf(stdout, "            done (%f seconds)\n\n", dt);
@@ -725,6 +775,7 @@ void MGPCG(mg_type *MG, int onLevel, int x_id, int F_id, double a, double b, dou
   const int jMax = 20;
   int j = 0, failed = 0, converged = 0;
 
+  krylov_count_begin();
   zero_vector(L, x_id);
   residual(L, r_id, x_id, F_id, a, b);
   if (L->must_subtract_mean == 1) { double m = mean(L, r_id); shift_vector(L, r_id, r_id, -m); }
@@ -763,7 +814,8 @@ void MGPCG(mg_type *MG, int onLevel, int x_id, int F_id, double a, double b, dou
     add_vectors(L, p_id, 1.0, z_id, beta, p_id);
     r_dot_z = r_dot_z_new;
   }
-  g_last.norm_of_F = norm_of_r0;  g_last.norm_of_residual = norm_of_r;  g_last_owner = MG;
+  krylov_count_collect(MG);
+  record_norms(MG, norm_of_r0, norm_of_r);
   const double dt = hpgmg_rt_wtime() - t0;
   MG->timers.MGSolve += dt;
   if (chatty) fprintf(stdout, "done (%f seconds)\n", dt);

@@ -27,8 +27,7 @@ extern "C" {
 int  hpgmg_b200_init(int device_ordinal);
 void hpgmg_b200_finalize(void);
 void hpgmg_b200_sync(void);                      /* drain the compute stream                    */
-const char *hpgmg_b200_backend(void);            /* "cuda-sm_100a" (or "cpu-emulation" in the
-                                                    kernel-debug harness under tests/)          */
+const char *hpgmg_b200_backend(void);            /* "cuda-sm_100a": there is no other backend    */
 
 /* ---- variant selection ----------------------------------------------------------------------
  * The reference picks the smoother at compile time (-DUSE_GSRB | -DUSE_CHEBY,

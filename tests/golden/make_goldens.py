@@ -24,7 +24,10 @@ import hpgmg_b200.api as api  # noqa: E402
 SOLVES = [(4, 1, False), (5, 1, False), (6, 1, False), (4, 8, False), (5, 8, False), (6, 8, False), (7, 8, False),
           (4, 27, False), (5, 27, False), (5, 64, False),
           (7, 27, False), (7, 64, False),      # = `7 8` per GPU on 4 / 8 GPUs (384^3 and 512^3: 4.5 and 10.6 GB on the host)
-          (5, 1, True), (5, 8, True), (6, 8, True), (5, 27, True)]
+          (5, 1, True), (5, 8, True), (6, 8, True), (5, 27, True),
+          (8, 8, False),                        # BASELINE config 4 on one GPU: 512^3 as 2^3 boxes of 256^3 (10 GB on the host)
+          (7, 64, True),                        # BASELINE config 5: Chebyshev, 512^3 as 4^3 boxes of 128^3 (the 1/2/4/8-GPU strong-scaling grid)
+          (7, 8, True)]                         # Chebyshev on the headline grid
 DECOMPOSITIONS = [(5, 8, 1), (5, 8, 2), (5, 8, 4), (5, 8, 8), (4, 1, 1), (6, 8, 1), (6, 8, 8), (4, 3, 9)]
 
 

@@ -402,22 +402,13 @@ def test_operator_timers_fill_the_reference_table(gpu_lib, capfd):
 
 # ------------------------------------------------------------------------- kernel variants behind switches
 VARIANTS = [
-    {"HPGMG_B200_TMA_CFG": "0"},                                  # 64x8 tiles, 2 blocks/SM
-    {"HPGMG_B200_TMA_CFG": "1"},                                  # 64x16 tiles, planes requested two steps ahead
-    {"HPGMG_B200_TMA_CFG": "3"},                                  # 32x16, two steps ahead
-    {"HPGMG_B200_TMA_CFG": "4"},                                  # 32x8, two steps ahead
-    {"HPGMG_B200_TMA_CFG": "5"}, {"HPGMG_B200_TMA_CFG": "6"},
     {"HPGMG_B200_TMA_BLOCKS": "37"},                              # uneven split: blocks own several partial columns
     {"HPGMG_B200_TMA_BLOCKS": "301", "HPGMG_B200_ZIGZAG": "0"},
     {"HPGMG_B200_DIAG": "0"},                                     # Dinv always from memory
-    {"HPGMG_B200_L2HINT": "2"},                                   # L2 eviction hints on the TMA loads
-    {"HPGMG_B200_TMA": "0"},                                      # the cp.async kernel
-    {"HPGMG_B200_TMA": "0", "HPGMG_B200_TILED_ASYNC": "0"},       # ... with register staging
-    {"HPGMG_B200_GENERIC_STENCIL": "1"},                          # one thread per cell
-    {"HPGMG_B200_PERSISTENT_SMOOTH": "8"},                        # small levels: one smooth = one cluster kernel
-    {"HPGMG_B200_PERSISTENT_SMOOTH": "1"},                        # ... cooperative grid barrier
+    {"HPGMG_B200_TMA": "0"},                                      # boxes >= 32^3 through the pair kernel
+    {"HPGMG_B200_GENERIC_STENCIL": "1"},                          # one thread per cell everywhere
+    {"HPGMG_B200_PAIR_KERNEL": "0"},                              # small boxes through the generic kernel
     {"HPGMG_B200_NO_COARSE_KERNEL": "1"},
-    {"HPGMG_B200_TMA_CFG": "7"},                                  # 32x8, three steps ahead
     {"HPGMG_B200_FUSE_NORM": "0"},                                # norm as a separate kernel after residual / R=F
     {"HPGMG_B200_INTERP_MARCH": "0"},                             # tiled interpolation on every level
     {"HPGMG_B200_INTERP_MARCH": "64"},                            # k-marching interpolation down to 16^3 boxes
