@@ -55,6 +55,7 @@ SIGNATURES = {
     "hpgmg_b200_bench_mark": (_V, [_I]), "hpgmg_b200_bench_elapsed_ms": (_D, [_I, _I]),
     "hpgmg_b200_profiler_start": (_V, []), "hpgmg_b200_profiler_stop": (_V, []),
     "hpgmg_b200_gsrb_sweep": (_V, [_LP, _I, _I, _I, _D, _D, _I]),
+    "hpgmg_b200_smoother_sweep": (_V, [_LP, _I, _I, _I, _D, _D, _I]),
     "hpgmg_b200_set_comm": (_V, [_I, _I, ALLGATHER_FN, BARRIER_FN, C.c_void_p]),
     "hpgmg_b200_comm_finalize": (_V, []), "hpgmg_b200_p2p_enabled": (_I, []),
     "hpgmg_b200_set_fmg_post_vcycles": (_V, [_I]),

@@ -28,14 +28,16 @@ __device__ __forceinline__ void quartic_pair(const double x1, const double x2, c
  * region that exchange_boundary would fill -- the image of that position inside the neighbouring
  * box (fused ghost fill, ghost.cu: same values, no dependency on the copy).  d0<d1<d2 (axis order) are
  * the inward strides of the normal axes; both boxes share the strides. */
-__device__ __forceinline__ void bc_v4_col1(const double *r, double *w, const int d0)
+/* e0<e1<e2: the same strides in the array that is written (they differ from d* when the column is written into a
+ * staged shared-memory tile, stencil_box.cuh) */
+__device__ __forceinline__ void bc_v4_col1(const double *r, double *w, const int d0, const int e0)
 {
   double n, f;
   quartic_pair(r[d0], r[2 * d0], r[3 * d0], r[4 * d0], n, f);
   w[0] = n;
-  w[-d0] = f;
+  w[-e0] = f;
 }
-__device__ __forceinline__ void bc_v4_col2(const double *r, double *w, const int d0, const int d1)
+__device__ __forceinline__ void bc_v4_col2(const double *r, double *w, const int d0, const int d1, const int e0, const int e1)
 {
   double n[4], f[4];
 #pragma unroll
@@ -47,11 +49,11 @@ __device__ __forceinline__ void bc_v4_col2(const double *r, double *w, const int
   quartic_pair(n[0], n[1], n[2], n[3], nn, nf);
   quartic_pair(f[0], f[1], f[2], f[3], fn, ff);
   w[0] = nn;
-  w[-d1] = nf;
-  w[-d0] = fn;
-  w[-d0 - d1] = ff;
+  w[-e1] = nf;
+  w[-e0] = fn;
+  w[-e0 - e1] = ff;
 }
-__device__ __forceinline__ void bc_v4_col3(const double *r, double *w, const int d0, const int d1, const int d2)
+__device__ __forceinline__ void bc_v4_col3(const double *r, double *w, const int d0, const int d1, const int d2, const int e0, const int e1, const int e2)
 {
   double nn[4], nf[4], fn[4], ff[4];
 #pragma unroll
@@ -71,14 +73,17 @@ __device__ __forceinline__ void bc_v4_col3(const double *r, double *w, const int
   quartic_pair(fn[0], fn[1], fn[2], fn[3], fnn, fnf);
   quartic_pair(ff[0], ff[1], ff[2], ff[3], ffn, fff);
   w[0] = nnn;
-  w[-d2] = nnf;
-  w[-d1] = nfn;
-  w[-d1 - d2] = nff;
-  w[-d0] = fnn;
-  w[-d0 - d2] = fnf;
-  w[-d0 - d1] = ffn;
-  w[-d0 - d1 - d2] = fff;
+  w[-e2] = nnf;
+  w[-e1] = nfn;
+  w[-e1 - e2] = nff;
+  w[-e0] = fnn;
+  w[-e0 - e2] = fnf;
+  w[-e0 - e1] = ffn;
+  w[-e0 - e1 - e2] = fff;
 }
+__device__ __forceinline__ void bc_v4_col1(const double *r, double *w, const int d0) { bc_v4_col1(r, w, d0, d0); }
+__device__ __forceinline__ void bc_v4_col2(const double *r, double *w, const int d0, const int d1) { bc_v4_col2(r, w, d0, d1, d0, d1); }
+__device__ __forceinline__ void bc_v4_col3(const double *r, double *w, const int d0, const int d1, const int d2) { bc_v4_col3(r, w, d0, d1, d2, d0, d1, d2); }
 
 /* ---- one column, quadratic: only the nearest ghost cell (boundary_fv.c:169, :206-209, :238-245) ---- */
 __device__ __forceinline__ double bc_v2_value(const double *r, const int m, const int d0, const int d1, const int d2)

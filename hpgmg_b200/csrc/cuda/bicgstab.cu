@@ -49,6 +49,7 @@ extern "C" int hpgmg_bicgstab_device(level_type *level, int x_id, int R_id, doub
   if (D->fill_nvec != level->numVectors) return 0;
   A.bc = D->fill[STENCIL_SHAPE_NO_CORNERS].bc;  A.nbc = D->fill[STENCIL_SHAPE_NO_CORNERS].nbc;
   A.x_id = x_id;  A.R_id = R_id;  A.a = a;  A.b = b;
+  A.ids = bottom_ids_identity();
   A.h2inv = 1.0 / (level->h * level->h);
   A.rtol = rtol;
   A.iters = hpgmg_rt_scalar_slots() + HPGMG_SLOT_KRYLOV;

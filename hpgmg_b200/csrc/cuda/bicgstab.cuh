@@ -13,11 +13,25 @@
 #define BOTTOM_MAX_CELLS (BOTTOM_MAX_DIM * BOTTOM_MAX_DIM * BOTTOM_MAX_DIM)
 #define BOTTOM_THREADS   256   /* the stand-alone kernel; the body works for any 1-D block that is a multiple of 32 (<=1024) */
 
+/* which vector of L plays which role: the identity (vector ids of the reference, bicgstab.c:17-24, defines.h:28-38) for the
+ * stand-alone kernel; the coarse-cycle kernel keeps only the vectors a cycle touches in shared memory and passes their slots */
+struct BottomIds {
+  int r0, r, p, q, s, t, Ap, As;
+  int dinv, temp, beta_i, beta_j, beta_k;
+};
+__host__ __device__ __forceinline__ BottomIds bottom_ids_identity()
+{
+  BottomIds I = { VECTORS_RESERVED + 0, VECTORS_RESERVED + 1, VECTORS_RESERVED + 2, VECTORS_RESERVED + 3, VECTORS_RESERVED + 4, VECTORS_RESERVED + 5,
+                  VECTORS_RESERVED + 6, VECTORS_RESERVED + 7, VECTOR_DINV, VECTOR_TEMP, VECTOR_BETA_I, VECTOR_BETA_J, VECTOR_BETA_K };
+  return I;
+}
+
 struct BottomArgs {
   DLevel L;
-  const FillBC *bc;             /* NO_CORNERS BC columns of the (single) box: flat table (device_level.cu) */
+  const FillBC *bc;             /* NO_CORNERS BC columns of the (single) box: flat table (device_level.cu); offsets are relative to a vector's start */
   int nbc;
   int x_id, R_id;
+  BottomIds ids;
   double a, b, h2inv, rtol;
   double *iters;                /* device scalar slot: iterations are added to it */
 };
@@ -51,7 +65,7 @@ __device__ static void b_apply(const BottomCtx &C, const int out_id, const int i
   __syncthreads();
   b_fill_ghosts(C, in_id);
   const DLevel &L = C.A.L;
-  const double *x = L.vec(0, in_id), *bi = L.vec(0, VECTOR_BETA_I), *bj = L.vec(0, VECTOR_BETA_J), *bk = L.vec(0, VECTOR_BETA_K);
+  const double *x = L.vec(0, in_id), *bi = L.vec(0, C.A.ids.beta_i), *bj = L.vec(0, C.A.ids.beta_j), *bk = L.vec(0, C.A.ids.beta_k);
   double *out = L.vec(0, out_id);
   const double *rhs = L.vec(0, rhs_id);
   for (int c = threadIdx.x; c < C.cells; c += blockDim.x) {
@@ -149,8 +163,8 @@ __device__ static void bicgstab_solve(const BottomArgs &A, double *prod, double 
 {
   BottomCtx C = { A, prod, red, A.L.dim, A.L.dim * A.L.dim * A.L.dim, A.L.jStride, A.L.kStride };
 
-  const int r0 = VECTORS_RESERVED + 0, r = VECTORS_RESERVED + 1, p = VECTORS_RESERVED + 2, q = VECTORS_RESERVED + 3;
-  const int s = VECTORS_RESERVED + 4, t = VECTORS_RESERVED + 5, Ap = VECTORS_RESERVED + 6, As = VECTORS_RESERVED + 7;
+  const int r0 = A.ids.r0, r = A.ids.r, p = A.ids.p, q = A.ids.q, s = A.ids.s, t = A.ids.t, Ap = A.ids.Ap, As = A.ids.As;
+  const int DINV = A.ids.dinv, TEMP = A.ids.temp;
   const int x_id = A.x_id;
   const int jMax = 200;
   int j = 0;
@@ -165,7 +179,7 @@ __device__ static void bicgstab_solve(const BottomArgs &A, double *prod, double 
   if (norm_of_r0 == 0.0) converged = true;
   while ((j < jMax) && !failed && !converged) {
     j++;
-    b_mul(C, q, 1.0, VECTOR_DINV, p);                     /* q = D^-1 p */
+    b_mul(C, q, 1.0, DINV, p);                     /* q = D^-1 p */
     b_apply(C, Ap, q, 0, 0);                              /* Ap = A q   */
     const double Ap_dot_r0 = b_dot(C, Ap, r0);
     if (Ap_dot_r0 == 0.0) { failed = true; break; }
@@ -176,7 +190,7 @@ __device__ static void bicgstab_solve(const BottomArgs &A, double *prod, double 
     const double norm_of_s = b_norm(C, s);
     if (norm_of_s == 0.0) { converged = true; break; }
     if (norm_of_s < A.rtol * norm_of_r0) { converged = true; break; }
-    b_mul(C, t, 1.0, VECTOR_DINV, s);                     /* t = D^-1 s */
+    b_mul(C, t, 1.0, DINV, s);                     /* t = D^-1 s */
     b_apply(C, As, t, 0, 0);                              /* As = A t   */
     const double As_dot_As = b_dot(C, As, As);
     const double As_dot_s = b_dot(C, As, s);
@@ -193,8 +207,8 @@ __device__ static void bicgstab_solve(const BottomArgs &A, double *prod, double 
     if (r_dot_r0_new == 0.0) { failed = true; break; }
     const double beta = (r_dot_r0_new / r_dot_r0) * (alpha / omega);
     if (isinf(beta)) { failed = true; break; }
-    b_add(C, VECTOR_TEMP, 1.0, p, -omega, Ap);
-    b_add(C, p, 1.0, r, beta, VECTOR_TEMP);
+    b_add(C, TEMP, 1.0, p, -omega, Ap);
+    b_add(C, p, 1.0, r, beta, TEMP);
     r_dot_r0 = r_dot_r0_new;
   }
   if (threadIdx.x == 0) atomicAdd(A.iters, (double)j);

@@ -135,6 +135,21 @@ struct FillTable {
   FillBC   *late;    int nlate;       /* columns that need data from another GPU first */
 };
 
+/* The same ghost fill (NO_CORNERS shape) binned by the compute tile that needs each value: the fused box kernels
+ * (stencil_box.cuh) stage a tile of x with its halo in shared memory and resolve the halo themselves -- cells of
+ * the neighbouring box and boundary-condition columns go straight into the staged tile -- so a sweep needs no
+ * separate fill kernel.  A record is listed under every tile whose halo contains its ghost cell(s).
+ * sidx: index of the (nearest) ghost cell in the staged tile [TK+4][TJ+4][TI+4]. */
+struct TileCopy { int src, dst, sidx, pad; };
+struct TileBC   { int src, dst, sidx, subtype; };
+struct TileRange { int copy0, ncopy, bc0, nbc; };
+struct TileTable {
+  TileRange *ranges;                            /* [nboxes * tiles per box], box-major, then k, j, i */
+  TileCopy  *copies;
+  TileBC    *bc;
+  int ntiles, ti, tj, tk;                       /* tile shape the table was binned for; ntiles == 0: not available */
+};
+
 /* device mirror hanging off level_type::fluxes */
 struct hpgmg_device_level {
   DLevel L;
@@ -144,6 +159,7 @@ struct hpgmg_device_level {
   DList  restriction[4][3];
   DList  interpolation[3];
   FillTable fill[STENCIL_MAX_SHAPES];
+  TileTable tile_fill;                          /* NO_CORNERS fill binned per compute tile (boxes of 4^3 .. 32^3 whose neighbours are all on this GPU) */
   int fill_nvec;                                /* numVectors the fill offsets were built for */
   int dinv_is_unit_diagonal;                    /* VECTOR_DINV was last written by rebuild_operator_blackbox with >= 4 colours per
                                                    dimension (no two cells of a colour inside one stencil): away from the boundary it

@@ -39,6 +39,11 @@ static T *upload_items(const std::vector<T> &v)
 
 static void free_fill_tables(hpgmg_device_level *D)
 {
+  TileTable &TT = D->tile_fill;
+  if (TT.ranges) CUDA_CHECK(cudaFree(TT.ranges));
+  if (TT.copies) CUDA_CHECK(cudaFree(TT.copies));
+  if (TT.bc) CUDA_CHECK(cudaFree(TT.bc));
+  memset(&TT, 0, sizeof(TT));
   for (int s = 0; s < STENCIL_MAX_SHAPES; s++) {
     FillTable &T = D->fill[s];
     if (T.copies) CUDA_CHECK(cudaFree(T.copies));
@@ -46,6 +51,71 @@ static void free_fill_tables(hpgmg_device_level *D)
     if (T.late) CUDA_CHECK(cudaFree(T.late));
     memset(&T, 0, sizeof(T));
   }
+}
+
+/* Tile shape of the fused box kernels (stencil_box.cuh) for boxes of n^3 cells; 0 if they do not cover the size */
+extern "C" int hpgmg_box_tile_shape(int n, int *ti, int *tj, int *tk)
+{
+  if (n != 4 && n != 8 && n != 16 && n != 32) return 0;
+  *ti = n < 16 ? n : 16;  *tj = n < 8 ? n : 8;  *tk = 4;
+  return 1;
+}
+
+/* Bin the NO_CORNERS fill of a level by compute tile (TileTable, common.cuh): every record goes to each tile whose
+ * staged halo tile [tk+4][tj+4][ti+4] contains its (nearest) ghost cell; a column's deeper ghost cells then lie in it too,
+ * because box ghost zones and tile halos are both 2 cells deep and tiles are at least 4 cells wide. */
+static void build_tile_table(level_type *level, hpgmg_device_level *D, const std::vector<FillCopy> &copies, const std::vector<FillBC> &bc)
+{
+  int ti, tj, tk;
+  const int n = level->box_dim, g = level->box_ghosts;
+  if (g != 2 || !hpgmg_box_tile_shape(n, &ti, &tj, &tk)) return;
+  const int jS = level->box_jStride, kS = level->box_kStride;
+  const long per_box = (long)level->numVectors * level->box_volume;
+  const int ni = n / ti, nj = n / tj, nk = n / tk, per = ni * nj * nk, ntiles = per * level->num_my_boxes;
+  const int sw = ti + 4, sh = tj + 4;
+  std::vector<std::vector<TileCopy> > tc((size_t)ntiles);
+  std::vector<std::vector<TileBC> > tb((size_t)ntiles);
+  auto for_each_tile = [&](int dst, auto &&emit) {
+    const int box = (int)(dst / per_box);
+    const int pos = (int)(dst - box * per_box);
+    const int c[3] = { pos % jS - g, (pos % kS) / jS - g, pos / kS - g };     /* the ghost cell, box coordinates */
+    const int t[3] = { ti, tj, tk }, cnt[3] = { ni, nj, nk };
+    int lo[3], hi[3];
+    for (int a = 0; a < 3; a++) {
+      /* tiles q with  q*t - 2 <= c < q*t + t + 2 */
+      lo[a] = (c[a] - t[a] - 1 + t[a] - 1 + 64 * t[a]) / t[a] - 64;             /* ceil((c - t - 1) / t), arguments kept positive */
+      hi[a] = (c[a] + 2 + 64 * t[a]) / t[a] - 64;                               /* floor((c + 2) / t) */
+      if (lo[a] < 0) lo[a] = 0;
+      if (hi[a] > cnt[a] - 1) hi[a] = cnt[a] - 1;
+    }
+    for (int qk = lo[2]; qk <= hi[2]; qk++) for (int qj = lo[1]; qj <= hi[1]; qj++) for (int qi = lo[0]; qi <= hi[0]; qi++) {
+      const int tile = box * per + qi + ni * (qj + nj * qk);
+      const int sidx = (c[0] - qi * ti + 2) + sw * ((c[1] - qj * tj + 2) + sh * (c[2] - qk * tk + 2));
+      emit(tile, sidx);
+    }
+  };
+  for (size_t e = 0; e < copies.size(); e++) {
+    const FillCopy &r = copies[e];
+    for_each_tile(r.dst, [&](int tile, int sidx) { TileCopy t = { r.src, r.dst, sidx, 0 }; tc[tile].push_back(t); });
+  }
+  for (size_t e = 0; e < bc.size(); e++) {
+    const FillBC &r = bc[e];
+    for_each_tile(r.dst, [&](int tile, int sidx) { TileBC t = { r.src, r.dst, sidx, r.subtype }; tb[tile].push_back(t); });
+  }
+  std::vector<TileRange> ranges((size_t)ntiles);
+  std::vector<TileCopy> allc;
+  std::vector<TileBC> allb;
+  for (int t = 0; t < ntiles; t++) {
+    TileRange R = { (int)allc.size(), (int)tc[t].size(), (int)allb.size(), (int)tb[t].size() };
+    ranges[t] = R;
+    allc.insert(allc.end(), tc[t].begin(), tc[t].end());
+    allb.insert(allb.end(), tb[t].begin(), tb[t].end());
+  }
+  TileTable &TT = D->tile_fill;
+  TT.ranges = upload_items(ranges);
+  TT.copies = upload_items(allc);
+  TT.bc = upload_items(allb);
+  TT.ntiles = ntiles;  TT.ti = ti;  TT.tj = tj;  TT.tk = tk;
 }
 
 /* Expand the local ghost-exchange list and the BC list of every shape into per-cell / per-column records
@@ -122,6 +192,8 @@ static void build_fill_tables(level_type *level, hpgmg_device_level *D)
     auto by_kind = [&](const FillBC &x, const FillBC &y) { return normals(x) < normals(y); };
     std::stable_sort(now.begin(), now.end(), by_kind);
     std::stable_sort(late.begin(), late.end(), by_kind);
+    if (s == STENCIL_SHAPE_NO_CORNERS && late.empty() && level->exchange_ghosts[s].num_sends == 0 && level->exchange_ghosts[s].num_recvs == 0)
+      build_tile_table(level, D, copies, now);
     FillTable &T = D->fill[s];
     T.copies = upload_items(copies);  T.ncopies = (int)copies.size();
     T.bc = upload_items(now);         T.nbc = (int)now.size();

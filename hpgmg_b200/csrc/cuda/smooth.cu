@@ -83,10 +83,11 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(const StencilArgs 
 }
 
 #include "stencil_tma.cuh"
+#include "stencil_box.cuh"
 #include <vector>
 
 /* switches kept for A/B parity checks (tests/test_gpu_parity.py::test_kernel_variants_give_the_same_bits); read once */
-static int g_force_generic = -1, g_tma = 1, g_tma_blocks = 0, g_zigzag = 1, g_diag = 1, g_pair_kernel = 1, g_tma_minplanes = 8;
+static int g_force_generic = -1, g_tma = 1, g_tma_blocks = 0, g_zigzag = 1, g_diag = 1, g_pair_kernel = 1, g_tma_minplanes = 8, g_box_fused_max = 16;
 
 static void stencil_env(void)
 {
@@ -98,6 +99,7 @@ static void stencil_env(void)
   if ((e = getenv("HPGMG_B200_ZIGZAG")) != NULL) g_zigzag = atoi(e);           /* 0: every sweep marches k upwards */
   if ((e = getenv("HPGMG_B200_DIAG")) != NULL) g_diag = atoi(e);               /* 0: Dinv always read from memory */
   if ((e = getenv("HPGMG_B200_PAIR_KERNEL")) != NULL) g_pair_kernel = atoi(e); /* 0: small boxes through the generic kernel */
+  if ((e = getenv("HPGMG_B200_BOX_FUSED_MAX")) != NULL) g_box_fused_max = atoi(e);   /* largest box the fill-fused kernels take (0: none, 32: also the TMA kernel's smallest size) */
 }
 
 /* ---- TMA descriptors: the level slab [box*vector][k][j][i] as a rank-4 tensor, one (W x rows) tile per copy ---- */
@@ -261,6 +263,50 @@ static void fill_ghosts(level_type *level, int id)
   hpgmg_fill_ghosts(level, id, STENCIL_SHAPE_NO_CORNERS, 4);    /* exchange_boundary + apply_BCs, fused */
 }
 
+/* ---- ghost fill + operator in one launch (stencil_box.cuh) where the level allows it ---------------- */
+template <int OP, int N, int TI, int TJ, int TK>
+static void launch_box(level_type *level, const StencilArgs &S, const int write_ghosts)
+{
+  hpgmg_device_level *D = HPGMG_DEV(level);
+  const TileTable &T = D->tile_fill;
+  BoxArgs A;
+  memset(&A, 0, sizeof(A));
+  A.L = D->L;  A.low = D->low;  A.ranges = T.ranges;  A.copies = T.copies;  A.bc = T.bc;
+  A.x_id = S.x_id;  A.rhs_id = S.rhs_id;  A.out_id = S.out_id;  A.sweep = S.sweep;  A.write_ghosts = write_ghosts;
+  A.b = S.b;  A.h2inv = 1.0 / (level->h * level->h);  A.c1 = S.c1;  A.c2 = S.c2;
+  typedef BoxCfg<N, TI, TJ, TK> C;
+  LAUNCH((stencil_box_kernel<OP, N, TI, TJ, TK>), D->L.nboxes * C::TILES, C::NT, 0, A);
+}
+
+/* 1 if the operator was enqueued as a fill-fused box kernel (then no separate ghost fill is needed) */
+template <int OP>
+static int try_launch_box(level_type *level, const StencilArgs &S, const int write_ghosts)
+{
+  stencil_env();
+  hpgmg_device_level *D = HPGMG_DEV(level);
+  const TileTable &T = D->tile_fill;
+  const int n = level->box_dim;
+  if (g_force_generic || n > g_box_fused_max || T.ntiles == 0 || level->num_my_boxes == 0) return 0;
+  if (D->fill_nvec != level->numVectors || level->box_ghosts != 2 || level->box_jStride != ((n + 4 + 3) / 4) * 4) return 0;
+  if (hpgmg_ablate(n < 64 ? 8 : 64)) return 1;
+  switch (n) {
+    case 4:  launch_box<OP, 4, 4, 4, 4>(level, S, write_ghosts); return 1;
+    case 8:  launch_box<OP, 8, 8, 8, 4>(level, S, write_ghosts); return 1;
+    case 16: launch_box<OP, 16, 16, 8, 4>(level, S, write_ghosts); return 1;
+    case 32: launch_box<OP, 32, 16, 8, 4>(level, S, write_ghosts); return 1;
+    default: return 0;
+  }
+}
+
+/* exchange_boundary + apply_BCs on x, then the operator: one fused launch on small boxes, fill kernel + operator kernel otherwise */
+template <int OP>
+static void fill_and_stencil(level_type *level, StencilArgs &A, const int write_ghosts)
+{
+  if (try_launch_box<OP>(level, A, write_ghosts)) return;
+  fill_ghosts(level, A.x_id);
+  launch_stencil<OP>(level, A);
+}
+
 extern "C" int stencil_get_radius(void) { return 2; }
 extern "C" int stencil_get_shape(void) { return STENCIL_SHAPE_NO_CORNERS; }
 
@@ -268,20 +314,18 @@ extern "C" void apply_op(level_type *level, int Ax_id, int x_id, double a, doubl
 {
   ProfileScope prof_(&level->timers.apply_op);
   hpgmg_note_vector_written(level, Ax_id);
-  fill_ghosts(level, x_id);
   StencilArgs A = {};
   A.x_id = x_id;  A.out_id = Ax_id;  A.a = a;  A.b = b;
-  launch_stencil<OP_APPLY>(level, A);
+  fill_and_stencil<OP_APPLY>(level, A, 1);
 }
 
 extern "C" void residual(level_type *level, int res_id, int x_id, int rhs_id, double a, double b)
 {
   ProfileScope prof_(&level->timers.residual);
   hpgmg_note_vector_written(level, res_id);
-  fill_ghosts(level, x_id);
   StencilArgs A = {};
   A.x_id = x_id;  A.rhs_id = rhs_id;  A.out_id = res_id;  A.a = a;  A.b = b;
-  launch_stencil<OP_RESIDUAL>(level, A);
+  fill_and_stencil<OP_RESIDUAL>(level, A, 1);
 }
 
 /* residual() followed by norm() of the result (mg.c:1316-1322, 1259-1262), the max taken inside the residual kernel
@@ -291,13 +335,12 @@ extern "C" void hpgmg_residual_norm_async(level_type *level, int res_id, int x_i
   static int fuse = -1;
   if (fuse < 0) { const char *e = getenv("HPGMG_B200_FUSE_NORM"); fuse = e ? atoi(e) : 1; }
   if (!fuse || hpgmg_rt_profile()) { residual(level, res_id, x_id, rhs_id, a, b); hpgmg_norm_async(level, res_id, slot); return; }
-  fill_ghosts(level, x_id);
   double *s = hpgmg_rt_scalar_slots() + slot;
   CUDA_CHECK(cudaMemsetAsync(s, 0, sizeof(double), g_stream));
   StencilArgs A = {};
   A.x_id = x_id;  A.rhs_id = rhs_id;  A.out_id = res_id;  A.a = a;  A.b = b;  A.norm_slot = s;
   g_norm_fused = false;
-  launch_stencil<OP_RESIDUAL>(level, A);
+  fill_and_stencil<OP_RESIDUAL>(level, A, 1);
   if (g_norm_fused) hpgmg_comm_allreduce_slot_max(level, slot);     /* MPI_Allreduce(MAX), misc.c:324; no-op on one rank */
   else hpgmg_norm_async(level, res_id, slot);
 }
@@ -307,15 +350,14 @@ static void smooth_gsrb(level_type *level, int x_id, int rhs_id, double a, doubl
   for (int s = 0; s < 6; s++) {                      /* NUM_SMOOTHS=3 -> RBRBRB (operators.fv4.c:177-180) */
     const int src = (s & 1) == 0 ? x_id : VECTOR_TEMP;
     const int dst = (s & 1) == 0 ? VECTOR_TEMP : x_id;
-    fill_ghosts(level, src);
     StencilArgs A = {};
     A.x_id = src;  A.rhs_id = rhs_id;  A.out_id = dst;  A.a = a;  A.b = b;  A.sweep = s;
     A.reverse = g_zigzag ? (s & 1) : 0;
-    launch_stencil<OP_GSRB>(level, A);
+    fill_and_stencil<OP_GSRB>(level, A, 0);
   }
 }
 
-/* one GSRB sweep kernel alone (no ghost fill): what bench.py times for the roofline line */
+/* one GSRB sweep kernel alone (no ghost fill) */
 extern "C" void hpgmg_b200_gsrb_sweep(level_type *level, int src_id, int dst_id, int rhs_id, double a, double b, int s)
 {
   StencilArgs A = {};
@@ -323,35 +365,54 @@ extern "C" void hpgmg_b200_gsrb_sweep(level_type *level, int src_id, int dst_id,
   launch_stencil<OP_GSRB>(level, A);
 }
 
-static void smooth_chebyshev(level_type *level, int x_id, int rhs_id, double a, double b)
+/* Chebyshev coefficients exactly as chebyshev.c:22-40 (degree 6, operators.fv4.c:184) */
+static void chebyshev_coefficients(const level_type *level, double c1[6], double c2[6])
 {
-  enum { DEGREE = 6 };                               /* CHEBYSHEV_DEGREE (operators.fv4.c:184) */
-  if (level->dominant_eigenvalue_of_DinvA <= 0.0 && level->my_rank == 0) fprintf(stderr, "dominant_eigenvalue_of_DinvA <= 0.0 !\n");
-  /* coefficients exactly as chebyshev.c:22-40 */
   double beta = 1.000 * level->dominant_eigenvalue_of_DinvA;
   double alpha = 0.125000 * beta;
   double theta = 0.5 * (beta + alpha);
   double delta = 0.5 * (beta - alpha);
   double sigma = theta / delta;
   double rho_n = 1 / sigma;
-  double c1[DEGREE], c2[DEGREE];
   c1[0] = 0.0;
   c2[0] = 1 / theta;
-  for (int s = 1; s < DEGREE; s++) {
+  for (int s = 1; s < 6; s++) {
     double rho_nm1 = rho_n;
     rho_n = 1.0 / (2.0 * sigma - rho_nm1);
     c1[s] = rho_n * rho_nm1;
     c2[s] = rho_n * 2.0 / delta;
   }
-  for (int s = 0; s < DEGREE; s++) {
+}
+
+static void chebyshev_sweep(level_type *level, int src, int dst, int rhs_id, double a, double b, const double c1, const double c2, const int with_fill)
+{
+  StencilArgs A = {};
+  A.x_id = src;  A.xm1_id = dst;  A.rhs_id = rhs_id;  A.out_id = dst;  A.a = a;  A.b = b;     /* x_{n-1} aliases x_{n+1} (chebyshev.c:75-80) */
+  A.c1 = c1;  A.c2 = c2;
+  if (with_fill) fill_and_stencil<OP_CHEBY>(level, A, 0);
+  else launch_stencil<OP_CHEBY>(level, A);
+}
+
+static void smooth_chebyshev(level_type *level, int x_id, int rhs_id, double a, double b)
+{
+  if (level->dominant_eigenvalue_of_DinvA <= 0.0 && level->my_rank == 0) fprintf(stderr, "dominant_eigenvalue_of_DinvA <= 0.0 !\n");
+  double c1[6], c2[6];
+  chebyshev_coefficients(level, c1, c2);
+  for (int s = 0; s < 6; s++) {
     const int src = (s & 1) == 0 ? x_id : VECTOR_TEMP;
     const int dst = (s & 1) == 0 ? VECTOR_TEMP : x_id;
-    fill_ghosts(level, src);
-    StencilArgs A = {};
-    A.x_id = src;  A.xm1_id = dst;  A.rhs_id = rhs_id;  A.out_id = dst;  A.a = a;  A.b = b;
-    A.c1 = c1[s % DEGREE];  A.c2 = c2[s % DEGREE];
-    launch_stencil<OP_CHEBY>(level, A);
+    chebyshev_sweep(level, src, dst, rhs_id, a, b, c1[s], c2[s], 1);
   }
+}
+
+/* one sweep kernel of the current smoother alone (no ghost fill): what bench.py times for the roofline line */
+extern "C" void hpgmg_b200_smoother_sweep(level_type *level, int src_id, int dst_id, int rhs_id, double a, double b, int s)
+{
+  if (hpgmg_rt_smoother() == HPGMG_SMOOTHER_CHEBY) {
+    double c1[6], c2[6];
+    chebyshev_coefficients(level, c1, c2);
+    chebyshev_sweep(level, src_id, dst_id, rhs_id, a, b, c1[s % 6], c2[s % 6], 0);
+  } else hpgmg_b200_gsrb_sweep(level, src_id, dst_id, rhs_id, a, b, s);
 }
 
 extern "C" void smooth(level_type *level, int x_id, int rhs_id, double a, double b)

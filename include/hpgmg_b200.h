@@ -107,6 +107,8 @@ void   hpgmg_b200_profiler_start(void);
 void   hpgmg_b200_profiler_stop(void);
 /* exactly one GSRB sweep kernel of smooth() (gsrb.c:41-129), without the ghost fill: dst = sweep s of src */
 void   hpgmg_b200_gsrb_sweep(level_type *level, int src_id, int dst_id, int rhs_id, double a, double b, int s);
+/* the same for whichever smoother is selected (Chebyshev: step s of chebyshev.c:51-97, x_{n-1} = dst) */
+void   hpgmg_b200_smoother_sweep(level_type *level, int src_id, int dst_id, int rhs_id, double a, double b, int s);
 
 /* ---- multi-GPU plumbing -----------------------------------------------------------------------
  * The reference talks MPI (exchange_boundary.c:33-97, restriction.c:128-192, misc.c:276,324).

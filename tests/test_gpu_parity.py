@@ -24,8 +24,10 @@ def close(a, b, rtol):
 
 
 # ------------------------------------------------------------------------------------------------ FMG
-GSRB = ["4 1", "5 1", "6 1", "4 8", "5 8", "6 8", "4 27", "5 27", "5 64", "7 8"]
-CHEBY = ["5 1", "5 8", "6 8", "5 27"]
+GSRB = ["4 1", "5 1", "6 1", "4 8", "5 8", "6 8", "4 27", "5 27", "5 64", "7 8",
+        "8 8"]                          # BASELINE config 4 on one GPU: 512^3 as 2^3 boxes of 256^3
+CHEBY = ["5 1", "5 8", "6 8", "5 27", "7 8",
+         "7 64"]                        # BASELINE config 5: 512^3 as 4^3 boxes of 128^3
 
 
 @pytest.mark.parametrize("cfg,smoother", [(c, "gsrb") for c in GSRB] + [(c, "cheby") for c in CHEBY])
@@ -225,6 +227,120 @@ def test_operator_equals_reference(gpu_lib, cfg, op):
             assert_level_equal(H, R, l, vid, where, op)
 
 
+@pytest.mark.skipif(not ob.have_ref(), reason="oracle/_ref (prebuilt reference library) not shipped")
+@pytest.mark.parametrize("log2", [7, 8])
+def test_large_single_box_operators_equal_reference(gpu_lib, log2):
+    """One 128^3 box (`7 1`: the box size behind the headline number) and one 256^3 box (`8 1`: BASELINE config 4):
+    smooth, residual, restriction and both interpolations cell by cell against the reference library -- the
+    TMA-staged kernels, their k-chunking and the k-marching interpolation at full box size."""
+    L = gpu_lib
+    U, E, Rr, T = api.VECTOR_U, api.VECTOR_E, api.VECTOR_R, api.VECTOR_TEMP
+    with api.Hierarchy(log2, 1, use_graphs=False) as H:
+        R = ob.RefHierarchy(log2, 1)
+        rng = np.random.default_rng(log2)
+        mirror_random(H, R, rng, (0,), (U, Rr, T))
+        mirror_random(H, R, rng, (1,), (E,))
+        l0, l1, r0, r1 = H.level(0), H.level(1), R.level(0), R.level(1)
+        L.smooth(l0, U, Rr, 0.0, 1.0); R.call("smooth", r0, U, Rr, 0.0, 1.0)
+        assert_level_equal(H, R, 0, U, "in", "smooth")
+        assert_level_equal(H, R, 0, T, "in", "smooth (TEMP)")
+        L.residual(l0, T, U, Rr, 0.0, 1.0); R.call("residual", r0, T, U, Rr, 0.0, 1.0)
+        assert_level_equal(H, R, 0, T, "in", "residual")
+        assert L.norm(l0, T) == R.call("norm", r0, T)
+        L.restriction(l1, Rr, l0, T, api.RESTRICT_CELL); R.call("restriction", r1, Rr, r0, T, api.RESTRICT_CELL)
+        assert_level_equal(H, R, 1, Rr, "in", "restriction")
+        L.interpolation_v2(l0, U, 1.0, l1, E); R.call("interpolation_v2", r0, U, 1.0, r1, E)
+        assert_level_equal(H, R, 0, U, "in", "interpolation_v2")
+        L.interpolation_v4(l0, T, 0.0, l1, E); R.call("interpolation_v4", r0, T, 0.0, r1, E)
+        assert_level_equal(H, R, 0, T, "in", "interpolation_v4")
+
+
+@pytest.mark.skipif(not ob.have_ref(), reason="oracle/_ref (prebuilt reference library) not shipped")
+def test_overwritten_diagonal_is_read_not_recomputed(gpu_lib):
+    """The TMA GSRB kernel forms Dinv = 1/Aii in registers only while VECTOR_DINV is known to come from
+    rebuild_operator_blackbox: once ANY operator of the API writes vector 5 the kernel must read it again."""
+    L = gpu_lib
+    U, Rr, DINV, E = api.VECTOR_U, api.VECTOR_R, api.VECTOR_DINV, api.VECTOR_E
+    for writer in ("scale", "mul", "add", "restriction"):
+        with api.Hierarchy(6, 1, use_graphs=False) as H:             # one 64^3 box: the TMA kernel, tiles away from the boundary
+            R = ob.RefHierarchy(6, 1)
+            rng = np.random.default_rng(11)
+            mirror_random(H, R, rng, (0, 1), (U, Rr, E))
+            lv, rl = (1, 1) if writer == "restriction" else (0, 0)
+            l, r = H.level(lv), R.level(rl)
+            if writer == "scale":
+                L.scale_vector(l, DINV, 0.5, DINV); R.call("scale_vector", r, DINV, 0.5, DINV)
+            elif writer == "mul":
+                L.mul_vectors(l, DINV, 1.25, DINV, DINV); R.call("mul_vectors", r, DINV, 1.25, DINV, DINV)
+            elif writer == "add":
+                L.add_vectors(l, DINV, 0.75, DINV, 0.0, E); R.call("add_vectors", r, DINV, 0.75, DINV, 0.0, E)
+            else:                                                    # level 1 (32^3): Dinv <- restriction of the fine Dinv
+                L.restriction(l, DINV, H.level(0), DINV, api.RESTRICT_CELL); R.call("restriction", r, DINV, R.level(0), DINV, api.RESTRICT_CELL)
+            L.smooth(l, U, Rr, 0.0, 1.0); R.call("smooth", r, U, Rr, 0.0, 1.0)
+            assert_level_equal(H, R, lv, U, "in", f"smooth after {writer} wrote Dinv")
+
+
+def test_recorded_solves_survive_reallocation_and_rebuild(gpu_lib):
+    """FMGSolve -> MGPCG (create_vectors on every level moves the slabs) -> FMGSolve -> rebuild_operator -> MGSolve ->
+    FMGSolve on ONE hierarchy: recorded graphs must not outlive what they captured."""
+    g = ob.goldens()["solves"]["5 8 gsrb"]
+    U, F = api.VECTOR_U, api.VECTOR_F
+    with api.Hierarchy(5, 8) as H:
+        assert H.fmg_solve(0)[0] == g["norms"][0]
+        gpu_lib.MGPCG(H.mg, 0, U, F, 0.0, 1.0, 1e-10)
+        pcg = api.download(H.level(0), 3, U).copy()
+        assert H.fmg_solve(0)[0] == g["norms"][0]
+        for l in range(1, H.num_levels):
+            gpu_lib.rebuild_operator(H.level(l), H.level(l - 1), 0.0, 1.0)
+        gpu_lib.zero_vector(H.level(0), U)
+        gpu_lib.MGSolve(H.mg, 0, U, F, 0.0, 1.0, 1e-10)
+        assert H.fmg_solve(0)[0] == g["norms"][0]
+        gpu_lib.MGPCG(H.mg, 0, U, F, 0.0, 1.0, 1e-10)
+        np.testing.assert_array_equal(pcg, api.download(H.level(0), 3, U))
+        bottom = H.level(H.num_levels - 1).contents
+        assert bottom.Krylov_iterations > 0
+
+
+def test_last_norms_are_kept_per_hierarchy(gpu_lib):
+    ga, gb = ob.goldens()["solves"]["4 8 gsrb"], ob.goldens()["solves"]["5 1 gsrb"]
+    with api.Hierarchy(4, 8) as A, api.Hierarchy(5, 1) as B:
+        A.fmg_solve(0)
+        B.fmg_solve(0)
+        assert gpu_lib.hpgmg_last_norm_of_residual(A.mg) == ga["norms"][0]
+        assert gpu_lib.hpgmg_last_norm_of_residual(B.mg) == gb["norms"][0]
+        assert gpu_lib.hpgmg_last_norm_of_F(A.mg) == ga["norm_of_F"] and gpu_lib.hpgmg_last_norm_of_F(B.mg) == gb["norm_of_F"]
+
+
+@pytest.mark.skipif(not ob.have_ref(), reason="oracle/_ref (prebuilt reference library) not shipped")
+def test_multibox_bottom_level_solves_without_recording(gpu_lib):
+    """MGBuild(minCoarseGridDim=16) on `4 8` stops at a 16^3 bottom level of 8 boxes: the bottom solve is the
+    host-driven BiCGStab (dots and norms read back every iteration), which must not be stream-captured."""
+    U, F = api.VECTOR_U, api.VECTOR_F
+    H = api.Hierarchy(4, 8, build_operator=False, use_graphs=True)
+    R = ob.RefHierarchy(4, 8, build_operator=False)
+    try:
+        gpu_lib.initialize_problem(H.level_h, H.h, 0.0, 1.0)
+        gpu_lib.rebuild_operator(H.level_h, None, 0.0, 1.0)
+        gpu_lib.MGBuild(H.mg, H.level_h, 0.0, 1.0, 16)
+        H.built = True
+        with ob.quiet():
+            R.L.initialize_problem(R.level_h, R.h, 0.0, 1.0)
+            R.L.rebuild_operator(R.level_h, None, 0.0, 1.0)
+            R.L.MGBuild(R.mg, R.level_h, 0.0, 1.0, 16)
+        R.built = True
+        assert H.num_levels == R.num_levels == 2
+        with ob.ref_threads(1):                  # the reference's dots are sums over tiles: order defined on one thread
+            R.call("zero_vector", R.level(0), U)
+            R.call("FMGSolve", R.mg, 0, U, F, 0.0, 1.0, 1e-10)
+        for _ in range(2):                       # twice: a recorded graph would be replayed the second time
+            gpu_lib.zero_vector(H.level(0), U)
+            gpu_lib.FMGSolve(H.mg, 0, U, F, 0.0, 1.0, 1e-10)
+            gpu_lib.hpgmg_b200_sync()
+            assert_level_equal(H, R, 0, U, "in", "FMGSolve with a multi-box bottom level")
+    finally:
+        H.close()
+
+
 @pytest.mark.skipif(not ob.have_ref(True), reason="oracle/_ref (prebuilt Chebyshev reference library) not shipped")
 def test_chebyshev_smoother_equals_reference(gpu_lib):
     with api.Hierarchy(4, 8, smoother=api.SMOOTHER_CHEBY, use_graphs=False) as H:
@@ -409,6 +525,9 @@ VARIANTS = [
     {"HPGMG_B200_GENERIC_STENCIL": "1"},                          # one thread per cell everywhere
     {"HPGMG_B200_PAIR_KERNEL": "0"},                              # small boxes through the generic kernel
     {"HPGMG_B200_NO_COARSE_KERNEL": "1"},
+    {"HPGMG_B200_COARSE_FAST": "0"},                              # coarse kernel: generic bodies instead of the size-specialised ones
+    {"HPGMG_B200_BOX_FUSED_MAX": "0"},                            # small boxes: separate ghost-fill kernel + operator kernel
+    {"HPGMG_B200_BOX_FUSED_MAX": "32"},                           # fill-fused box kernel also on 32^3 boxes (instead of the TMA kernel)
     {"HPGMG_B200_FUSE_NORM": "0"},                                # norm as a separate kernel after residual / R=F
     {"HPGMG_B200_INTERP_MARCH": "0"},                             # tiled interpolation on every level
     {"HPGMG_B200_INTERP_MARCH": "64"},                            # k-marching interpolation down to 16^3 boxes
