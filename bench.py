@@ -254,15 +254,16 @@ def ours(args):
 
     # ---- end to end through the C-ABI with HOST buffers (pinned): H2D f, zero u, FMGSolve, D2H u ----
     Lc = lvl.contents
-    nbytes = Lc.num_my_boxes * Lc.box_volume * 8
+    import numpy as np
+    cells = Lc.box_dim ** 3
+    nbytes = Lc.num_my_boxes * cells * 8                     # the cells of this rank's boxes, dense
     e2e = None
     if nbytes > 0:
         f_host = L.hpgmg_b200_host_alloc_pinned(nbytes)
         u_host = L.hpgmg_b200_host_alloc_pinned(nbytes)
-        vol = Lc.box_volume
         for b in range(Lc.num_my_boxes):
-            arr = api.download(lvl, b, api.VECTOR_F).reshape(-1)
-            C.memmove(f_host + b * vol * 8, arr.ctypes.data, vol * 8)
+            arr = np.ascontiguousarray(api.interior(lvl, api.download(lvl, b, api.VECTOR_F))).reshape(-1)
+            C.memmove(f_host + b * cells * 8, arr.ctypes.data, cells * 8)
         for _ in range(2):
             L.hpgmg_fmg_solve_host(H.mg, 0, api.VECTOR_U, api.VECTOR_F, H.a, H.b, 1e-10, f_host, u_host)
         barrier()
@@ -276,6 +277,10 @@ def ours(args):
                "ms_per_step": 1e3 * e2e_s, "f_cycle_norm": e2e_norm}
         if gold is not None and e2e_norm != gold:
             raise SystemExit(f"bench.py: end-to-end F-cycle residual norm {e2e_norm!r} differs from the reference's {gold!r}")
+        u_back = np.ctypeslib.as_array((C.c_double * cells).from_address(u_host + (Lc.num_my_boxes - 1) * cells * 8))
+        u_dev = api.interior(lvl, api.download(lvl, Lc.num_my_boxes - 1, api.VECTOR_U)).reshape(-1)
+        if not np.array_equal(u_back, u_dev):
+            raise SystemExit("bench.py: the solution downloaded by the end-to-end call differs from the one on the device")
         L.hpgmg_b200_host_free_pinned(f_host)
         L.hpgmg_b200_host_free_pinned(u_host)
 

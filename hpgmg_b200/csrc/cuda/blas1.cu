@@ -181,6 +181,73 @@ __global__ void __launch_bounds__(256) copy_norm_kernel(const DLevel L, const in
   }
 }
 
+/* ---- dense <-> padded: the cells of every box as one contiguous [box][k][j][i] array (the end-to-end solve's staging buffers) ---- */
+/* MODE 0: box vector <- dense.  MODE 1: dense <- box vector.  MODE 2: F <- dense, R <- 1.0*dense, max|dense| (the first step of
+ * FMGSolve, mg.c:1259-1269, fused with the unpack of the uploaded right-hand side) */
+template <int MODE>
+__global__ void __launch_bounds__(256) dense_kernel(const DLevel L, const int id, const int id2, double *__restrict__ dense, double *__restrict__ slot)
+{
+  PDL_WAIT();
+  const int n = L.dim, box = blockIdx.y;
+  const int hn = n / 2, pairs = hn * n * n;                /* even n only */
+  double *__restrict__ v = L.vec(box, id);
+  double *__restrict__ v2 = (MODE == 2) ? L.vec(box, id2) : nullptr;
+  double2 *__restrict__ d = reinterpret_cast<double2 *>(dense + (size_t)box * n * n * n);
+  double m = 0.0;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < pairs; q += gridDim.x * blockDim.x) {
+    const int p = q % hn, j = (q / hn) % n, k = q / (hn * n);
+    const int ijk = 2 * p + j * L.jStride + k * L.kStride;
+    if constexpr (MODE == 1) { d[q] = *reinterpret_cast<const double2 *>(v + ijk); }
+    else {
+    const double2 a = d[q];
+    *reinterpret_cast<double2 *>(v + ijk) = a;
+    if constexpr (MODE == 2) {
+      *reinterpret_cast<double2 *>(v2 + ijk) = make_double2(1.0 * a.x, 1.0 * a.y);
+      const double f0 = fabs(a.x), f1 = fabs(a.y);
+      if (f0 > m) m = f0;
+      if (f1 > m) m = f1;
+    }
+    }
+  }
+  if constexpr (MODE == 2) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double other = __shfl_down_sync(0xffffffffu, m, o);
+    if (other > m) m = other;
+  }
+  __shared__ double wmax[8];
+  if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) if (wmax[w] > m) m = wmax[w];
+    atomic_max_nonneg(slot, m);
+  }
+  }
+}
+template <int MODE>
+static void launch_dense(level_type *level, int id, int id2, double *dense, double *slot)
+{
+  const DLevel &L = dl_of(level);
+  if (L.nboxes == 0) return;
+  if (L.dim & 1) { fprintf(stderr, "hpgmg_b200: dense pack/unpack needs an even box size\n"); exit(1); }
+  const int pairs = (L.dim / 2) * L.dim * L.dim;
+  int bx = (pairs + 1023) / 1024;
+  if (bx > 592) bx = 592;
+  LAUNCH(dense_kernel<MODE>, dim3(bx, L.nboxes), 256, 0, L, id, id2, dense, slot);
+}
+extern "C" void hpgmg_unpack_async(level_type *level, int id, const double *dense)
+{ hpgmg_note_vector_written(level, id); launch_dense<0>(level, id, id, const_cast<double *>(dense), NULL); }
+extern "C" void hpgmg_pack_async(level_type *level, int id, double *dense) { launch_dense<1>(level, id, id, dense, NULL); }
+extern "C" void hpgmg_unpack_copy_norm_async(level_type *level, int id_f, int id_r, const double *dense, int slot)
+{
+  hpgmg_note_vector_written(level, id_f);  hpgmg_note_vector_written(level, id_r);
+  double *s = hpgmg_rt_scalar_slots() + slot;
+  CUDA_CHECK(cudaMemsetAsync(s, 0, sizeof(double), g_stream));
+  g_launches++;
+  launch_dense<2>(level, id_f, id_r, const_cast<double *>(dense), s);
+  hpgmg_comm_allreduce_slot_max(level, slot);
+}
+
 extern "C" void hpgmg_norm_async(level_type *level, int id_a, int slot);
 /* norm(level, id_a) into `slot` and scale_vector(level, id_c, 1.0, id_a) */
 extern "C" void hpgmg_copy_norm_async(level_type *level, int id_c, int id_a, int slot)

@@ -36,6 +36,10 @@ static double *g_scalars = NULL;            /* device, HPGMG_NUM_SCALARS doubles
 static double *g_scalars_host = NULL;       /* pinned mirror                      */
 static cudaEvent_t g_ev0, g_ev1;
 static double g_last_device_seconds = 0.0;
+static void *g_staging[2] = { NULL, NULL };     /* dense cells of f / u of the end-to-end solve */
+static size_t g_staging_bytes[2] = { 0, 0 };
+static cudaStream_t g_side_stream = 0, g_main_stream_saved = 0;
+static cudaEvent_t g_ev_fork = 0, g_ev_join = 0;
 
 /* Layout-only mode: the host-side data model (decomposition, block lists, level table) can be built
  * and inspected on a machine without a GPU.  Allocations become inaccessible address-space
@@ -110,6 +114,8 @@ extern "C" void hpgmg_b200_finalize(void)
   cudaStreamSynchronize(g_stream);
   hpgmg_graph_drop_all(NULL);
   cudaFree(g_scalars);  cudaFreeHost(g_scalars_host);
+  for (int w = 0; w < 2; w++) { if (g_staging[w]) cudaFree(g_staging[w]); g_staging[w] = NULL; g_staging_bytes[w] = 0; }
+  if (g_side_stream) { cudaStreamDestroy(g_side_stream); cudaEventDestroy(g_ev_fork); cudaEventDestroy(g_ev_join); g_side_stream = 0; }
   cudaEventDestroy(g_ev0);  cudaEventDestroy(g_ev1);
   cudaStreamDestroy(g_stream);
   g_stream = 0;  g_initialised = 0;
@@ -310,49 +316,40 @@ extern "C" double hpgmg_b200_bench_elapsed_ms(int from, int to)
 extern "C" unsigned long long hpgmg_b200_kernel_launches(void) { return g_launches; }
 
 /* ------------------------------------------------------------------------------------------ */
-/* End-to-end solve with HOST buffers: H2D of f, zero u, FMGSolve, D2H of u (bench.py's e2e).  Whole padded boxes
- * travel as single contiguous copies.  HPGMG_B200_E2E_CELLS_ONLY=1 moves only the cells (9 % fewer bytes) as a
- * pitched 3-D copy: measured 21.9 ms vs 11.7 ms per `7 8` solve -- 1 KB rows run the copy engine far below the PCIe
- * rate -- so it is off. */
-static void copy_box_cells(level_type *L, double *dev, double *host, int to_device)
-{
-  const size_t jS = (size_t)L->box_jStride, rows = (size_t)(L->box_dim + 2 * L->box_ghosts), n = (size_t)L->box_dim, g = (size_t)L->box_ghosts;
-  cudaMemcpy3DParms P;
-  memset(&P, 0, sizeof(P));
-  const cudaPitchedPtr d = make_cudaPitchedPtr(dev, jS * sizeof(double), jS, rows), h = make_cudaPitchedPtr(host, jS * sizeof(double), jS, rows);
-  P.srcPtr = to_device ? h : d;
-  P.dstPtr = to_device ? d : h;
-  P.srcPos = P.dstPos = make_cudaPos(g * sizeof(double), g, g);
-  P.extent = make_cudaExtent(n * sizeof(double), n, n);
-  P.kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
-  CUDA_CHECK(cudaMemcpy3DAsync(&P, g_stream));
-}
+/* Plumbing of the end-to-end solve with HOST buffers (hpgmg_fmg_solve_host, mg.c): two device staging buffers that hold
+ * the dense cells of f and u, and a side stream on which the download of u runs while the compute stream finishes the
+ * solve (final residual + norm).  Fork and join are event edges, so they are recorded into the solve's CUDA graph. */
 
-extern "C" double hpgmg_fmg_solve_host(mg_type *all_grids, int onLevel, int u_id, int F_id, double a, double b,
-                                       double rtol, const double *f_host, double *u_host)
+extern "C" void *hpgmg_rt_staging(int which, size_t bytes)
 {
-  level_type *L = all_grids->levels[onLevel];
-  const size_t vol = (size_t)L->box_volume;
-  static int whole = -1;
-  if (whole < 0) { const char *e = getenv("HPGMG_B200_E2E_CELLS_ONLY"); whole = (e && atoi(e)) ? 0 : 1; }
-  for (int box = 0; box < L->num_my_boxes; box++) {
-    if (whole) hpgmg_rt_copy_h2d(L->my_boxes[box].vectors[F_id], f_host + (size_t)box * vol, vol * sizeof(double));
-    else copy_box_cells(L, L->my_boxes[box].vectors[F_id], const_cast<double *>(f_host) + (size_t)box * vol, 1);
+  require_init("staging");
+  if (bytes > g_staging_bytes[which]) {
+    CUDA_CHECK(cudaStreamSynchronize(g_stream));
+    hpgmg_graph_drop_all(NULL);                        /* recorded end-to-end solves hold the old buffer */
+    if (g_staging[which]) CUDA_CHECK(cudaFree(g_staging[which]));
+    CUDA_CHECK(cudaMalloc(&g_staging[which], bytes));
+    g_staging_bytes[which] = bytes;
   }
-  zero_vector(L, u_id);
-  FMGSolve(all_grids, onLevel, u_id, F_id, a, b, rtol);
-  for (int box = 0; box < L->num_my_boxes; box++) {
-    if (whole) hpgmg_rt_copy_d2h(u_host + (size_t)box * vol, L->my_boxes[box].vectors[u_id], vol * sizeof(double));
-    else copy_box_cells(L, L->my_boxes[box].vectors[u_id], u_host + (size_t)box * vol, 0);
-  }
-  hpgmg_rt_sync();
-  return hpgmg_last_norm_of_residual(all_grids);
+  return g_staging[which];
 }
-/* bytes one hpgmg_fmg_solve_host call moves in each direction on this rank */
-extern "C" unsigned long long hpgmg_fmg_solve_host_bytes(mg_type *all_grids, int onLevel)
+/* from here on the library's launches and copies go to the side stream, which first waits for everything enqueued so far */
+extern "C" void hpgmg_rt_side_begin(void)
 {
-  level_type *L = all_grids->levels[onLevel];
-  const char *e = getenv("HPGMG_B200_E2E_CELLS_ONLY");
-  const unsigned long long per_box = (e && atoi(e)) ? (unsigned long long)L->box_dim * L->box_dim * L->box_dim : (unsigned long long)L->box_volume;
-  return per_box * sizeof(double) * (unsigned long long)L->num_my_boxes;
+  if (!g_side_stream) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&g_side_stream, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&g_ev_fork, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&g_ev_join, cudaEventDisableTiming));
+  }
+  CUDA_CHECK(cudaEventRecord(g_ev_fork, g_stream));
+  CUDA_CHECK(cudaStreamWaitEvent(g_side_stream, g_ev_fork, 0));
+  g_main_stream_saved = g_stream;
+  g_stream = g_side_stream;
 }
+/* back to the compute stream; the side work keeps running */
+extern "C" void hpgmg_rt_side_end(void)
+{
+  CUDA_CHECK(cudaEventRecord(g_ev_join, g_stream));
+  g_stream = g_main_stream_saved;
+}
+/* the compute stream waits for the side work */
+extern "C" void hpgmg_rt_side_join(void) { CUDA_CHECK(cudaStreamWaitEvent(g_stream, g_ev_join, 0)); }

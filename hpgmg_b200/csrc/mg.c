@@ -594,10 +594,14 @@ static void enqueue_residual_norm(level_type *L, int e_id, int F_id, double a, d
 /* One F-cycle (mg.c:1237-1344): ||F||, R=F, restrict R to the bottom, bottom solve, then for
  * every level going up: 4th-order interpolation of the coarse solution as initial guess followed
  * by one V-cycle.  Solves in place (e_id == u_id). */
+static void enqueue_fcycle_after_rhs(mg_type *MG, int onLevel, int e_id, int R_id, double a, double b);
 static void enqueue_fcycle(mg_type *MG, int onLevel, int e_id, int R_id, int F_id, double a, double b)
 {
-  level_type *L = MG->levels[onLevel];
-  hpgmg_copy_norm_async(L, R_id, F_id, HPGMG_SLOT_NORM_F);
+  hpgmg_copy_norm_async(MG->levels[onLevel], R_id, F_id, HPGMG_SLOT_NORM_F);      /* ||F|| and R = F (mg.c:1265-1269) */
+  enqueue_fcycle_after_rhs(MG, onLevel, e_id, R_id, a, b);
+}
+static void enqueue_fcycle_after_rhs(mg_type *MG, int onLevel, int e_id, int R_id, double a, double b)
+{
   for (int l = onLevel; l < MG->num_levels - 1; l++)
     restriction(MG->levels[l + 1], R_id, MG->levels[l], R_id, RESTRICT_CELL);
   int bottom = MG->num_levels - 1;
@@ -667,6 +671,62 @@ void FMGSolve(mg_type *MG, int onLevel, int u_id, int F_id, double a, double b, 
   const double dt = hpgmg_rt_wtime() - t0;
   MG->timers.MGSolve += dt;
   if (chatty) fprintf(stdout, "done (%f seconds)\n", dt);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* FMGSolve with HOST buffers -- the end-to-end call (bench.py's e2e): f_host and u_host hold the CELLS of this rank's boxes,
+ * dense, box-major, [k][j][i] per box.  One recorded graph does: upload f into a staging buffer; unpack it into F fused
+ * with the first step of FMGSolve (||F||, R = F); zero u; the F-cycle; then the download of u (pack kernel + copy on a
+ * side stream) OVERLAPPED with the final residual and its norm on the compute stream.  Returns the F-cycle residual norm. */
+static long long hash_pointer(const void *p) { return (long long)((unsigned long long)(size_t)p * 0x9E3779B97F4A7C15ull); }
+unsigned long long hpgmg_fmg_solve_host_bytes(mg_type *MG, int onLevel)
+{
+  const level_type *L = MG->levels[onLevel];
+  return (unsigned long long)L->num_my_boxes * L->box_dim * L->box_dim * L->box_dim * sizeof(double);
+}
+double hpgmg_fmg_solve_host(mg_type *MG, int onLevel, int u_id, int F_id, double a, double b, double rtol, const double *f_host, double *u_host)
+{
+  (void)rtol;
+  level_type *L = MG->levels[onLevel];
+  const size_t bytes = (size_t)hpgmg_fmg_solve_host_bytes(MG, onLevel);
+  if ((L->box_dim & 1) || !L->active) {                 /* odd boxes: no 16-byte pairs; plain path */
+    fprintf(stderr, "hpgmg_fmg_solve_host: needs an even box size and an active level\n");
+    exit(1);
+  }
+  MG->MGSolves_performed++;
+  const int e_id = u_id, R_id = VECTOR_R;
+  double *stage_f = bytes ? (double *)hpgmg_rt_staging(0, bytes) : NULL;       /* (re)allocated before any recording starts */
+  double *stage_u = bytes ? (double *)hpgmg_rt_staging(1, bytes) : NULL;
+  const int capturable = solve_is_capturable(MG, L);
+  const long long key = solve_key(7, onLevel, u_id, F_id, a, b) ^ hash_pointer(f_host) ^ (hash_pointer(u_host) << 1);
+  hpgmg_rt_timer_start();
+  if (!capturable || hpgmg_graph_begin(MG, key)) {
+    if (bytes) hpgmg_rt_copy_h2d(stage_f, f_host, bytes);
+    hpgmg_rt_zero_scalar(HPGMG_SLOT_KRYLOV);
+    zero_vector(L, u_id);                                                        /* hpgmg-fv.c:78 */
+    hpgmg_unpack_copy_norm_async(L, F_id, R_id, stage_f, HPGMG_SLOT_NORM_F);
+    enqueue_fcycle_after_rhs(MG, onLevel, e_id, R_id, a, b);
+    if (L->must_subtract_mean == 1) {                                            /* periodic: the mean is removed from u first (mg.c:1317-1320) */
+      enqueue_residual_norm(L, e_id, F_id, a, b);
+      hpgmg_pack_async(L, u_id, stage_u);
+      if (bytes) hpgmg_rt_copy_d2h(u_host, stage_u, bytes);
+    } else {
+      hpgmg_rt_side_begin();                                                     /* u is final: download it ... */
+      hpgmg_pack_async(L, u_id, stage_u);
+      if (bytes) hpgmg_rt_copy_d2h(u_host, stage_u, bytes);
+      hpgmg_rt_side_end();
+      enqueue_residual_norm(L, e_id, F_id, a, b);                                /* ... while the residual and its norm are computed */
+      hpgmg_rt_side_join();
+    }
+    if (capturable) hpgmg_graph_end(MG, key);
+  }
+  hpgmg_rt_timer_stop();
+  count_vcycle_visits(MG, onLevel);
+  double s[3];
+  hpgmg_rt_read_scalars(s, HPGMG_SLOT_NORM_F, 3);
+  MG->levels[MG->num_levels - 1]->Krylov_iterations += (int)s[2];
+  record_norms(MG, s[0], s[1]);
+  return s[1];
 }
 
 /* ------------------------------------------------------------------------------------------ */

@@ -96,6 +96,16 @@ void   hpgmg_comm_transfer_wait(level_type *level_send, communicator_type *Cs, l
 int  hpgmg_coarse_chain_eligible(mg_type *MG, int from);
 void hpgmg_coarse_cycle(mg_type *MG, int from, int mode_ftail, int zero_bottom, int e_id, int R_id, double a, double b);
 
+/* end-to-end solve with host buffers (mg.c: hpgmg_fmg_solve_host): dense staging buffers, the side stream the download runs
+ * on, and the kernels that move cells between a dense [box][k][j][i] buffer and the padded boxes (blas1.cu) */
+void *hpgmg_rt_staging(int which, size_t bytes);
+void  hpgmg_rt_side_begin(void);
+void  hpgmg_rt_side_end(void);
+void  hpgmg_rt_side_join(void);
+void  hpgmg_unpack_copy_norm_async(level_type *level, int id_f, int id_r, const double *dense, int slot);   /* F = dense; R = 1.0*F; slot = max|F| */
+void  hpgmg_pack_async(level_type *level, int id, double *dense);
+void  hpgmg_unpack_async(level_type *level, int id, const double *dense);
+
 /* event timing of a solve body */
 void hpgmg_rt_timer_start(void);
 void hpgmg_rt_timer_stop(void);

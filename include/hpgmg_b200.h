@@ -82,10 +82,11 @@ void hpgmg_upload_box_vector(level_type *level, int box, int id, const double *h
 void *hpgmg_b200_host_alloc_pinned(size_t bytes);
 void  hpgmg_b200_host_free_pinned(void *p);
 
-/* FMGSolve with HOST buffers (the end-to-end call of bench.py): f and u are num_my_boxes x volume doubles,
- * box-major, each box in the device layout (ghost shell included).  Uploads f into F_id, zeroes u_id, runs
- * FMGSolve (mg.c:1237), downloads u_id into u.  Returns the F-cycle residual max-norm (the number
- * mg.c:1325-1329 prints).  hpgmg_fmg_solve_host_bytes: bytes moved per call and direction. */
+/* FMGSolve with HOST buffers (the end-to-end call of bench.py): f and u hold the CELLS of this rank's boxes, dense:
+ * num_my_boxes x box_dim^3 doubles, box-major (the level's box order), [k][j][i] inside a box; pinned memory
+ * (hpgmg_b200_host_alloc_pinned) makes the copies asynchronous.  Uploads f into F_id, zeroes u_id, runs FMGSolve
+ * (mg.c:1237) and downloads u_id into u; the download overlaps the final residual and norm.  Returns the F-cycle residual
+ * max-norm (the number mg.c:1325-1329 prints).  hpgmg_fmg_solve_host_bytes: bytes moved per call and direction. */
 double hpgmg_fmg_solve_host(mg_type *all_grids, int onLevel, int u_id, int F_id, double a, double b,
                             double rtol, const double *f_host, double *u_host);
 unsigned long long hpgmg_fmg_solve_host_bytes(mg_type *all_grids, int onLevel);

@@ -94,18 +94,37 @@ def test_coarse_kernel_equals_multilaunch_path(gpu_lib, cfg, smoother):
 
 
 def test_fmg_solve_host_buffers(gpu_lib):
-    """The end-to-end entry point with HOST buffers (what bench.py's e2e times)."""
+    """The end-to-end entry point with HOST buffers (what bench.py's e2e times): dense cells in, dense cells out; the
+    download of u overlaps the final residual, and a replayed recording must give the same answer as the first call."""
     with api.Hierarchy(5, 8) as H:
         r, _ = H.fmg_solve(0)
-        Lc = H.level(0).contents
-        vol, nb = Lc.box_volume, Lc.num_my_boxes
-        f = np.concatenate([api.download(H.level(0), b, api.VECTOR_F).reshape(-1) for b in range(nb)])
-        u_ref = np.concatenate([api.download(H.level(0), b, api.VECTOR_U).reshape(-1) for b in range(nb)])
-        u = np.zeros(nb * vol)
-        r2 = gpu_lib.hpgmg_fmg_solve_host(H.mg, 0, api.VECTOR_U, api.VECTOR_F, 0.0, 1.0, 1e-10, f.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p))
-        assert r2 == r
-        np.testing.assert_array_equal(u, u_ref)
-        assert gpu_lib.hpgmg_fmg_solve_host_bytes(H.mg, 0) == nb * vol * 8
+        lvl = H.level(0)
+        Lc = lvl.contents
+        n, nb = Lc.box_dim, Lc.num_my_boxes
+        f = np.concatenate([np.ascontiguousarray(api.interior(lvl, api.download(lvl, b, api.VECTOR_F))).reshape(-1) for b in range(nb)])
+        u_ref = np.concatenate([np.ascontiguousarray(api.interior(lvl, api.download(lvl, b, api.VECTOR_U))).reshape(-1) for b in range(nb)])
+        assert gpu_lib.hpgmg_fmg_solve_host_bytes(H.mg, 0) == nb * n ** 3 * 8
+        for b in range(nb):                                  # the call must bring F itself: wipe the device copy
+            api.upload(lvl, b, api.VECTOR_F, np.zeros(Lc.box_volume))
+        for attempt in range(3):                             # first call records, later calls replay
+            u = np.full(nb * n ** 3, np.nan)
+            r2 = gpu_lib.hpgmg_fmg_solve_host(H.mg, 0, api.VECTOR_U, api.VECTOR_F, 0.0, 1.0, 1e-10, f.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p))
+            assert r2 == r, attempt
+            np.testing.assert_array_equal(u, u_ref)
+        assert gpu_lib.hpgmg_last_norm_of_residual(H.mg) == r
+    gpu_lib.hpgmg_b200_use_graphs(0)
+    try:                                                     # the same without recording (plain stream launches on two streams)
+        with api.Hierarchy(4, 8, use_graphs=False) as H:
+            r, _ = H.fmg_solve(0)
+            lvl = H.level(0)
+            nb, n = lvl.contents.num_my_boxes, lvl.contents.box_dim
+            f = np.concatenate([np.ascontiguousarray(api.interior(lvl, api.download(lvl, b, api.VECTOR_F))).reshape(-1) for b in range(nb)])
+            u_ref = np.concatenate([np.ascontiguousarray(api.interior(lvl, api.download(lvl, b, api.VECTOR_U))).reshape(-1) for b in range(nb)])
+            u = np.zeros(nb * n ** 3)
+            assert gpu_lib.hpgmg_fmg_solve_host(H.mg, 0, api.VECTOR_U, api.VECTOR_F, 0.0, 1.0, 1e-10, f.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p)) == r
+            np.testing.assert_array_equal(u, u_ref)
+    finally:
+        gpu_lib.hpgmg_b200_use_graphs(1)
 
 
 # ------------------------------------------------------------------------------ operator by operator
