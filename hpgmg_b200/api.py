@@ -59,6 +59,7 @@ SIGNATURES = {
     "hpgmg_b200_set_comm": (_V, [_I, _I, ALLGATHER_FN, BARRIER_FN, C.c_void_p]),
     "hpgmg_b200_comm_finalize": (_V, []), "hpgmg_b200_p2p_enabled": (_I, []),
     "hpgmg_b200_set_fmg_post_vcycles": (_V, [_I]),
+    "hpgmg_b200_set_agglomeration": (_V, [_I]), "hpgmg_b200_get_agglomeration": (_I, []),
     # level.h
     "create_level": (_V, [_LP, _I, _I, _I, _I, _I, _I, _I]), "destroy_level": (_V, [_LP]),
     "create_vectors": (_V, [_LP, _I]), "reset_level_timers": (_V, [_LP]),

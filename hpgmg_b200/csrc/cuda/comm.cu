@@ -97,43 +97,88 @@ extern "C" int hpgmg_comm_size(void) { return g_nranks; }
 extern "C" void hpgmg_comm_barrier(void) { if (g_nranks > 1 && g_barrier) { hpgmg_rt_sync(); g_barrier(g_comm_ctx); } }
 
 /* ---- reductions --------------------------------------------------------------------------------- */
-static void require_world(const level_type *level, const char *what)
+/* MPI_Allreduce of ONE double over the ranks that share a level (misc.c:276,324,373 on level->MPI_COMM_ALLREDUCE, the
+ * sub-communicator of mg.c:979-997: ranks 0 .. num_ranks-1 of the level) or over all ranks (rebuild.c:195).
+ *
+ * With peer memory: every participant stores its value, tagged with the reduction's sequence number, into a mailbox in
+ * each participant's arena (the 16-byte LL slot of p2p.cuh: value and flag arrive together) and then polls its own mailbox
+ * until all values are there; they are combined in rank order, so every rank gets the same bits.  One kernel of one warp,
+ * sequence numbers in device memory: capturable, no host involvement, a few microseconds instead of an ncclAllReduce launch.
+ * Each subset size has its own mailboxes and counter, so ranks outside a sub-communicator never fall out of step.  Two
+ * slot sets alternate by sequence parity: a rank can only be one reduction ahead of a peer, because finishing reduction k
+ * needs the peer's value k, which the peer sends after it has finished k-1. */
+#include "p2p.cuh"
+#define AR_MAX_RANKS 32
+struct ARPeers { uint4 *mbox[AR_MAX_RANKS]; };          /* rank p's mailbox array, as mapped into this process */
+static uint4 *g_ar_mbox = NULL;                           /* mine: [subset size][parity][sender] */
+static unsigned long long *g_ar_seq = NULL;               /* device: reductions completed, per subset size */
+static ARPeers g_ar_peers;
+__host__ __device__ static inline size_t ar_slot(const int n, const int parity, const int sender) { return ((size_t)(n * 2 + parity)) * AR_MAX_RANKS + sender; }
+
+__global__ void ll_allreduce_kernel(double *value, const ARPeers P, const int n, const int my_rank, const int op, unsigned long long *seq)
 {
-  if (!g_comm) { fprintf(stderr, "hpgmg_b200: %s on a %d-rank level but no communicator was installed (hpgmg_b200_set_comm)\n", what, level->num_ranks); exit(1); }
-  if (level->num_ranks != g_nranks) {
-    fprintf(stderr, "hpgmg_b200: %s on a level shared by %d of %d ranks is not supported (sub-communicators, mg.c:979-997)\n", what, level->num_ranks, g_nranks);
+  PDL_WAIT();
+  __shared__ double vals[AR_MAX_RANKS];
+  const unsigned long long k = *(volatile unsigned long long *)seq;
+  const unsigned flag = (unsigned)(k + 1);
+  const int parity = (int)(k & 1), t = threadIdx.x;
+  const double mine = *(volatile double *)value;
+  if (t < n) ll_store(P.mbox[t] + ar_slot(n, parity, my_rank), mine, flag);
+  if (t < n) vals[t] = ll_load(P.mbox[my_rank] + ar_slot(n, parity, t), flag);
+  __syncwarp();
+  if (t == 0) {
+    double r = vals[0];
+    for (int q = 1; q < n; q++) r = op ? r + vals[q] : (vals[q] > r ? vals[q] : r);
+    *value = r;
+    *seq = k + 1;
+  }
+}
+
+static int g_p2p_enabled = 0;
+static void require_comm(const char *what)
+{
+  if (!g_comm) { fprintf(stderr, "hpgmg_b200: %s across ranks but no communicator was installed (hpgmg_b200_set_comm)\n", what); exit(1); }
+}
+/* reduce the device scalar `s` in place over ranks 0..n-1 (op 0: max, 1: sum); stream-ordered */
+static void allreduce_device_scalar(double *s, const int n, const int op, const char *what)
+{
+  if (n <= 1 || g_nranks <= 1 || g_rank >= n) return;       /* ranks outside the sub-communicator keep their local value */
+  require_comm(what);
+  if (g_p2p_enabled && n <= AR_MAX_RANKS) {
+    LAUNCH(ll_allreduce_kernel, 1, 32, 0, s, g_ar_peers, n, g_rank, op, g_ar_seq + n);
+    return;
+  }
+  if (n != g_nranks) {
+    fprintf(stderr, "hpgmg_b200: %s over %d of %d ranks needs the peer-memory path (CUDA IPC unavailable here)\n", what, n, g_nranks);
     exit(1);
   }
+  NCCL_CHECK(N.AllReduce(s, s, 1, ncclFloat64, op ? ncclSum : ncclMax, g_comm, g_stream));
+  g_launches++;
 }
 
 extern "C" void hpgmg_comm_allreduce_slot_max(level_type *level, int slot)
 {
-  if (level->num_ranks <= 1 || g_nranks <= 1) return;
-  require_world(level, "norm");
-  double *s = hpgmg_rt_scalar_slots() + slot;
-  NCCL_CHECK(N.AllReduce(s, s, 1, ncclFloat64, ncclMax, g_comm, g_stream));
-  g_launches++;
+  allreduce_device_scalar(hpgmg_rt_scalar_slots() + slot, level->num_ranks, 0, "norm");
 }
 
 static double allreduce_host_value(level_type *level, double v, int op, const char *what, int world)
 {
-  if (g_nranks <= 1 || (!world && level->num_ranks <= 1)) return v;
-  if (world) { if (!g_comm) { fprintf(stderr, "hpgmg_b200: %s needs a communicator\n", what); exit(1); } }
-  else require_world(level, what);
+  const int n = world ? g_nranks : level->num_ranks;
+  if (g_nranks <= 1 || n <= 1 || g_rank >= n) return v;
   const int slot = HPGMG_SLOT_SCRATCH + 3;
   double *s = hpgmg_rt_scalar_slots() + slot;
   CUDA_CHECK(cudaMemcpyAsync(s, &v, sizeof(double), cudaMemcpyHostToDevice, g_stream));
   CUDA_CHECK(cudaStreamSynchronize(g_stream));
-  NCCL_CHECK(N.AllReduce(s, s, 1, ncclFloat64, op, g_comm, g_stream));
+  allreduce_device_scalar(s, n, op, what);
   double r = 0.0;
   hpgmg_rt_read_scalars(&r, slot, 1);
   return r;
 }
 /* over the ranks that share the level (MPI_COMM_ALLREDUCE of the reference) */
-extern "C" double hpgmg_comm_allreduce_max(level_type *level, double v) { return allreduce_host_value(level, v, ncclMax, "max-reduction", 0); }
-extern "C" double hpgmg_comm_allreduce_sum(level_type *level, double v) { return allreduce_host_value(level, v, ncclSum, "sum-reduction", 0); }
+extern "C" double hpgmg_comm_allreduce_max(level_type *level, double v) { return allreduce_host_value(level, v, 0, "max-reduction", 0); }
+extern "C" double hpgmg_comm_allreduce_sum(level_type *level, double v) { return allreduce_host_value(level, v, 1, "sum-reduction", 0); }
 /* over ALL ranks, whatever the level's rank count: the reference reduces lambda_max on MPI_COMM_WORLD (rebuild.c:195) */
-extern "C" double hpgmg_comm_allreduce_max_world(level_type *level, double v) { return allreduce_host_value(level, v, ncclMax, "max-reduction (world)", 1); }
+extern "C" double hpgmg_comm_allreduce_max_world(level_type *level, double v) { return allreduce_host_value(level, v, 0, "max-reduction (world)", 1); }
 
 /* ---- point-to-point ------------------------------------------------------------------------------ */
 /* ghost exchange of one level: receive into recv_buffers, send from send_buffers (both sides use the
@@ -182,8 +227,6 @@ extern "C" void hpgmg_comm_transfer_wait(level_type *level_send, communicator_ty
 #include <map>
 #include <vector>
 
-#include "p2p.cuh"
-
 struct P2PHost {
   P2PPlan *plan;                                   /* device */
   blockCopy_type *pack, *unpack;                   /* device copies: write.ptr -> remote buffers; subtype = neighbour index */
@@ -194,7 +237,11 @@ static char *g_arena = NULL;
 static size_t g_arena_size = 0, g_arena_used = 0;
 static std::vector<char *> g_peer_arena;          /* my mapping of every rank's arena */
 static std::map<communicator_type *, P2PHost> g_p2p;
-static int g_p2p_enabled = 0;
+struct XferPlan;
+struct XferHost { XferPlan *plan; blockCopy_type *pack; int npack; };          /* inter-level transfers over peer memory (below) */
+static std::map<communicator_type *, XferHost> g_xfer_send, g_xfer_recv;
+static size_t g_arena_base = 0;                   /* permanent allocations (reduction mailboxes) end here */
+static long g_arena_live = 0;                     /* allocations handed out and not yet freed */
 
 extern "C" int hpgmg_rt_is_comm_memory(const void *p) { return g_arena && (const char *)p >= g_arena && (const char *)p < g_arena + g_arena_size; }
 
@@ -206,10 +253,30 @@ extern "C" void *hpgmg_rt_alloc_comm(size_t bytes)
     fprintf(stderr, "hpgmg_b200: comm arena exhausted (%zu of %zu bytes used, %zu requested); set HPGMG_B200_COMM_ARENA_MB\n", g_arena_used, g_arena_size, bytes);
     exit(1);
   }
-  void *p = g_arena + g_arena_used;               /* never reused, and the arena was zeroed (synchronously) when it was created:
-                                                     a stream-ordered memset here could run AFTER a fast peer's first store */
+  void *p = g_arena + g_arena_used;               /* bump allocation out of memory that was zeroed synchronously (at creation or at the last
+                                                     collective reset): a stream-ordered memset here could run AFTER a fast peer's first store */
   g_arena_used += need;
+  g_arena_live++;
   return p;
+}
+extern "C" void hpgmg_rt_free_comm(void *p) { (void)p; if (g_arena_live > 0) g_arena_live--; }
+
+/* Collective (called by every rank at the start of create_level): once NO rank holds live arena memory any more -- all
+ * hierarchies destroyed -- the arena is zeroed and handed out from the start again, so a process that builds and destroys
+ * many hierarchies does not run out.  Zeroing matters: LL slots are recognised by their sequence flags. */
+extern "C" void hpgmg_comm_recycle_arena(void)
+{
+  if (!g_arena || g_nranks <= 1 || !g_allgather) return;
+  int mine = (g_arena_live == 0 && g_p2p.empty() && g_xfer_send.empty() && g_xfer_recv.empty()) ? 1 : 0, all_free = 1;
+  std::vector<int> everyone((size_t)g_nranks);
+  g_allgather(&mine, everyone.data(), sizeof(int), g_comm_ctx);
+  for (int r = 0; r < g_nranks; r++) all_free &= everyone[r];
+  if (!all_free || g_arena_used == g_arena_base) return;
+  hpgmg_rt_sync();
+  if (g_barrier) g_barrier(g_comm_ctx);             /* nobody is still storing into a peer's old slots */
+  CUDA_CHECK(cudaMemset(g_arena + g_arena_base, 0, g_arena_used - g_arena_base));
+  g_arena_used = g_arena_base;
+  if (g_barrier) g_barrier(g_comm_ctx);
 }
 
 /* called from hpgmg_b200_set_comm once NCCL is up: create, export and map the arenas */
@@ -238,6 +305,15 @@ static void p2p_setup(void)
   g_allgather(&ok, oks.data(), sizeof(int), g_comm_ctx);
   for (int r = 0; r < g_nranks; r++) ok &= oks[r];
   if (!ok) { if (g_rank == 0) fprintf(stderr, "hpgmg_b200: CUDA IPC peer mapping unavailable; using NCCL send/recv for halos\n"); g_p2p_enabled = 0; return; }
+  /* reduction mailboxes: the first thing in every rank's arena, hence at the same offset everywhere */
+  const size_t mbox_bytes = sizeof(uint4) * ar_slot(AR_MAX_RANKS + 1, 0, 0);
+  g_ar_mbox = (uint4 *)hpgmg_rt_alloc_comm(mbox_bytes);
+  g_arena_live--;                                    /* permanent */
+  g_arena_base = g_arena_used;
+  for (int r = 0; r < AR_MAX_RANKS; r++) g_ar_peers.mbox[r] = (r < g_nranks) ? (uint4 *)(g_peer_arena[r] + ((char *)g_ar_mbox - g_arena)) : NULL;
+  CUDA_CHECK(cudaMalloc(&g_ar_seq, sizeof(unsigned long long) * (AR_MAX_RANKS + 1)));
+  CUDA_CHECK(cudaMemset(g_ar_seq, 0, sizeof(unsigned long long) * (AR_MAX_RANKS + 1)));
+  if (g_barrier) g_barrier(g_comm_ctx);             /* every arena is zeroed and mapped before anybody stores into one */
   g_p2p_enabled = 1;
 }
 
@@ -330,6 +406,173 @@ int hpgmg_comm_p2p_lookup(level_type *level, int shape, const blockCopy_type **p
   return 1;
 }
 
+/* ================================================================================================
+ * Inter-level transfers (restriction / interpolation where box ownership changes) over peer memory.
+ *
+ * One message per (sender, receiver) pair per transfer, as in the reference (restriction.c:128-192,
+ * interpolation_v2.c:235-300): the sender's pack kernel writes the message straight into the RECEIVER's receive
+ * buffer (the pack list is re-pointed at the peer mapping of that buffer), then a one-warp kernel publishes it:
+ * system-scope fence, then the message number into a flag word next to the buffer.  The receiver's wait kernel
+ * spins on the flag, its unpack kernel reads local memory, and an ack kernel stores the message number back into
+ * the sender's arena; the sender does not overwrite the (single) buffer before it has seen the ack of the previous
+ * message -- which in a V- or F-cycle arrived long ago, because restriction and interpolation between two levels
+ * alternate.  All counters live in device memory and are advanced by the kernels, so the whole exchange is
+ * recorded into the solve's CUDA graph; versus grouped ncclSend/ncclRecv it removes ~20 us per transfer.
+ * ================================================================================================ */
+struct XferPlan {                                  /* device-resident; one per communicator SIDE */
+  unsigned long long seq;                          /* messages completed on this side */
+  int n;                                           /* neighbours */
+  unsigned long long *remote[P2P_MAX_NEIGHBOURS];  /* sender: receiver's flag word; receiver: sender's ack word */
+  unsigned long long *local[P2P_MAX_NEIGHBOURS];   /* sender: my ack word (the receiver stores into it); receiver: my flag word */
+};
+
+__global__ void xfer_pre_kernel(XferPlan *P)       /* sender: the receivers have consumed my previous message */
+{
+  PDL_WAIT();
+  const unsigned long long k = *(volatile unsigned long long *)&P->seq;
+  if ((int)threadIdx.x < P->n) while (*(volatile unsigned long long *)P->local[threadIdx.x] < k) { }
+}
+__global__ void xfer_post_kernel(XferPlan *P)      /* sender: publish message k (the pack kernel before me wrote it) */
+{
+  PDL_WAIT();
+  const unsigned long long k = *(volatile unsigned long long *)&P->seq;
+  __threadfence_system();
+  if ((int)threadIdx.x < P->n) *(volatile unsigned long long *)P->remote[threadIdx.x] = k + 1;
+  __syncwarp();
+  if (threadIdx.x == 0) P->seq = k + 1;
+}
+__global__ void xfer_wait_kernel(XferPlan *P)      /* receiver: message k has arrived from everybody */
+{
+  PDL_WAIT();
+  const unsigned long long k = *(volatile unsigned long long *)&P->seq;
+  if ((int)threadIdx.x < P->n) while (*(volatile unsigned long long *)P->local[threadIdx.x] < k + 1) { }
+  __threadfence_system();
+}
+__global__ void xfer_ack_kernel(XferPlan *P)       /* receiver: the unpack kernel before me is done with the buffers */
+{
+  PDL_WAIT();
+  const unsigned long long k = *(volatile unsigned long long *)&P->seq;
+  if ((int)threadIdx.x < P->n) *(volatile unsigned long long *)P->remote[threadIdx.x] = k + 1;
+  __syncwarp();
+  if (threadIdx.x == 0) P->seq = k + 1;
+}
+
+struct XferWire {                                  /* what a rank tells the others about one transfer */
+  int nrecv, nsend;
+  int recv_from[P2P_MAX_NEIGHBOURS], recv_size[P2P_MAX_NEIGHBOURS];
+  long long data_off[P2P_MAX_NEIGHBOURS], flag_off[P2P_MAX_NEIGHBOURS];     /* in the receiver's arena */
+  int send_to[P2P_MAX_NEIGHBOURS];
+  long long ack_off[P2P_MAX_NEIGHBOURS];                                    /* in the sender's arena */
+};
+
+/* collective: every rank calls it for every (sending communicator, receiving communicator) pair of the hierarchy, in the same order */
+extern "C" void hpgmg_comm_register_transfer(communicator_type *Cs, communicator_type *Cr)
+{
+  if (!g_p2p_enabled || g_nranks <= 1 || hpgmg_rt_layout_only()) return;
+  static int off = -1;
+  if (off < 0) { const char *e = getenv("HPGMG_B200_NCCL_TRANSFERS"); off = (e && atoi(e)) ? 1 : 0; }
+  if (off) return;
+  const int nsend = Cs ? Cs->num_sends : 0, nrecv = Cr ? Cr->num_recvs : 0;
+  XferWire mine;
+  memset(&mine, 0, sizeof(mine));
+  int fits = nsend <= P2P_MAX_NEIGHBOURS && nrecv <= P2P_MAX_NEIGHBOURS;
+  for (int n = 0; fits && n < nrecv; n++) if (!hpgmg_rt_is_comm_memory(Cr->recv_buffers[n])) fits = 0;
+  XferPlan hs, hr;
+  memset(&hs, 0, sizeof(hs));  memset(&hr, 0, sizeof(hr));
+  if (fits) {
+    mine.nrecv = nrecv;  mine.nsend = nsend;
+    for (int n = 0; n < nrecv; n++) {
+      unsigned long long *flag = (unsigned long long *)hpgmg_rt_alloc_comm(sizeof(unsigned long long));
+      hr.local[n] = flag;
+      mine.recv_from[n] = Cr->recv_ranks[n];  mine.recv_size[n] = Cr->recv_sizes[n];
+      mine.data_off[n] = (long long)((char *)Cr->recv_buffers[n] - g_arena);
+      mine.flag_off[n] = (long long)((char *)flag - g_arena);
+    }
+    for (int n = 0; n < nsend; n++) {
+      unsigned long long *ack = (unsigned long long *)hpgmg_rt_alloc_comm(sizeof(unsigned long long));
+      hs.local[n] = ack;
+      mine.send_to[n] = Cs->send_ranks[n];
+      mine.ack_off[n] = (long long)((char *)ack - g_arena);
+    }
+  } else mine.nrecv = -1;
+  std::vector<XferWire> all((size_t)g_nranks);
+  g_allgather(&mine, all.data(), sizeof(XferWire), g_comm_ctx);
+  for (int r = 0; r < g_nranks; r++) if (all[r].nrecv < 0) return;            /* somebody cannot: everybody keeps NCCL for this one */
+
+  if (nsend > 0) {
+    std::vector<blockCopy_type> pack(Cs->blocks[0], Cs->blocks[0] + Cs->num_blocks[0]);
+    std::vector<char *> remote_data((size_t)nsend);
+    for (int n = 0; n < nsend; n++) {
+      const int R = Cs->send_ranks[n];
+      int found = -1;
+      for (int m = 0; m < all[R].nrecv; m++) if (all[R].recv_from[m] == g_rank) found = m;
+      if (found < 0 || all[R].recv_size[found] != Cs->send_sizes[n]) {
+        fprintf(stderr, "hpgmg_b200: transfer: rank %d expects %d doubles from rank %d, which sends %d\n", R, found < 0 ? -1 : all[R].recv_size[found], g_rank, Cs->send_sizes[n]);
+        exit(1);
+      }
+      remote_data[n] = g_peer_arena[R] + all[R].data_off[found];
+      hs.remote[n] = (unsigned long long *)(g_peer_arena[R] + all[R].flag_off[found]);
+    }
+    for (size_t e = 0; e < pack.size(); e++) {                                /* re-point the pack list at the receivers' buffers */
+      int n = -1;
+      for (int m = 0; m < nsend; m++)
+        if ((char *)pack[e].write.ptr >= (char *)Cs->send_buffers[m] && (char *)pack[e].write.ptr < (char *)(Cs->send_buffers[m] + Cs->send_sizes[m])) n = m;
+      if (n < 0) { fprintf(stderr, "hpgmg_b200: transfer pack entry without a send buffer\n"); exit(1); }
+      pack[e].write.ptr = (double *)(remote_data[n] + ((char *)pack[e].write.ptr - (char *)Cs->send_buffers[n]));
+    }
+    XferHost H;
+    memset(&H, 0, sizeof(H));
+    hs.n = nsend;
+    H.npack = (int)pack.size();
+    if (H.npack) { CUDA_CHECK(cudaMalloc(&H.pack, pack.size() * sizeof(blockCopy_type))); CUDA_CHECK(cudaMemcpy(H.pack, pack.data(), pack.size() * sizeof(blockCopy_type), cudaMemcpyHostToDevice)); }
+    CUDA_CHECK(cudaMalloc(&H.plan, sizeof(XferPlan)));
+    CUDA_CHECK(cudaMemcpy(H.plan, &hs, sizeof(XferPlan), cudaMemcpyHostToDevice));
+    g_xfer_send[Cs] = H;
+  }
+  if (nrecv > 0) {
+    for (int n = 0; n < nrecv; n++) {
+      const int S = Cr->recv_ranks[n];
+      int found = -1;
+      for (int q = 0; q < all[S].nsend; q++) if (all[S].send_to[q] == g_rank) found = q;
+      if (found < 0) { fprintf(stderr, "hpgmg_b200: transfer: rank %d does not send to rank %d, which expects a message\n", S, g_rank); exit(1); }
+      hr.remote[n] = (unsigned long long *)(g_peer_arena[S] + all[S].ack_off[found]);
+    }
+    XferHost H;
+    memset(&H, 0, sizeof(H));
+    hr.n = nrecv;
+    CUDA_CHECK(cudaMalloc(&H.plan, sizeof(XferPlan)));
+    CUDA_CHECK(cudaMemcpy(H.plan, &hr, sizeof(XferPlan), cudaMemcpyHostToDevice));
+    g_xfer_recv[Cr] = H;
+  }
+}
+
+extern "C" void hpgmg_comm_unregister_transfer(communicator_type *C)
+{
+  for (int side = 0; side < 2; side++) {
+    std::map<communicator_type *, XferHost> &M = side ? g_xfer_recv : g_xfer_send;
+    std::map<communicator_type *, XferHost>::iterator it = M.find(C);
+    if (it == M.end()) continue;
+    hpgmg_rt_sync();
+    if (it->second.pack) cudaFree(it->second.pack);
+    cudaFree(it->second.plan);
+    M.erase(it);
+  }
+}
+
+/* sender side: 1 if this communicator's messages travel over peer memory; *pack = the re-pointed pack list */
+extern "C" int hpgmg_comm_xfer_send_lookup(communicator_type *Cs, const blockCopy_type **pack, int *npack)
+{
+  std::map<communicator_type *, XferHost>::iterator it = g_xfer_send.find(Cs);
+  if (it == g_xfer_send.end()) return 0;
+  *pack = it->second.pack;  *npack = it->second.npack;
+  return 1;
+}
+extern "C" int hpgmg_comm_xfer_recv_lookup(communicator_type *Cr) { return g_xfer_recv.find(Cr) != g_xfer_recv.end(); }
+extern "C" void hpgmg_comm_xfer_pre(communicator_type *Cs)  { LAUNCH(xfer_pre_kernel, 1, 32, 0, g_xfer_send[Cs].plan); }
+extern "C" void hpgmg_comm_xfer_post(communicator_type *Cs) { LAUNCH(xfer_post_kernel, 1, 32, 0, g_xfer_send[Cs].plan); }
+extern "C" void hpgmg_comm_xfer_wait(communicator_type *Cr) { LAUNCH(xfer_wait_kernel, 1, 32, 0, g_xfer_recv[Cr].plan); }
+extern "C" void hpgmg_comm_xfer_ack(communicator_type *Cr)  { LAUNCH(xfer_ack_kernel, 1, 32, 0, g_xfer_recv[Cr].plan); }
+
 extern "C" void hpgmg_b200_p2p_finalize(void)
 {
   if (!g_arena) return;
@@ -338,6 +581,8 @@ extern "C" void hpgmg_b200_p2p_finalize(void)
   g_peer_arena.clear();
   if (g_barrier) g_barrier(g_comm_ctx);             /* nobody frees while a peer may still have it mapped */
   cudaFree(g_arena);
-  g_arena = NULL;  g_arena_size = g_arena_used = 0;  g_p2p_enabled = 0;
+  if (g_ar_seq) cudaFree(g_ar_seq);
+  g_ar_seq = NULL;  g_ar_mbox = NULL;
+  g_arena = NULL;  g_arena_size = g_arena_used = g_arena_base = 0;  g_arena_live = 0;  g_p2p_enabled = 0;
 }
 extern "C" int hpgmg_b200_p2p_enabled(void) { return g_p2p_enabled; }

@@ -182,7 +182,7 @@ extern "C" void hpgmg_rt_free(void *p)
     if (it != g_reservations.end()) { munmap(p, it->second); g_reservations.erase(it); }
     return;
   }
-  if (hpgmg_rt_is_comm_memory(p)) return;             /* bump-allocated from the peer-visible arena: released with the arena */
+  if (hpgmg_rt_is_comm_memory(p)) { hpgmg_rt_free_comm(p); return; }   /* bump-allocated from the peer-visible arena: recycled when every rank is done with it */
   CUDA_CHECK(cudaStreamSynchronize(g_stream));
   CUDA_CHECK(cudaFree(p));
 }

@@ -91,7 +91,18 @@ extern "C" void restriction(level_type *level_c, int id_c, level_type *level_f, 
   hpgmg_device_level *Df = HPGMG_DEV(level_f), *Dc = HPGMG_DEV(level_c);
   communicator_type *Cf = &level_f->restriction[restrictionType], *Cc = &level_c->restriction[restrictionType];
   const int remote = (Cf->num_sends > 0) || (Cc->num_recvs > 0);
-  if (remote) {
+  /* peer-memory path (comm.cu): the pack list writes into the receivers' buffers; registered collectively, so both ends agree */
+  DList peer_pack = { NULL, 0 };
+  const int p2p_send = Cf->num_sends > 0 && hpgmg_comm_xfer_send_lookup(Cf, (const blockCopy_type **)&peer_pack.blocks, &peer_pack.n);
+  const int p2p_recv = Cc->num_recvs > 0 && hpgmg_comm_xfer_recv_lookup(Cc);
+  const int p2p = p2p_send || p2p_recv;
+  if (remote && p2p) {
+    if (p2p_send) {
+      hpgmg_comm_xfer_pre(Cf);
+      run_restriction_list(level_c, id_c, level_f, id_f, peer_pack, restrictionType);                            /* pack into the peers */
+      hpgmg_comm_xfer_post(Cf);
+    }
+  } else if (remote) {
     run_restriction_list(level_c, id_c, level_f, id_f, Df->restriction[restrictionType][0], restrictionType);   /* pack */
     hpgmg_comm_transfer(level_f, Cf, level_c, Cc, 0x5);
   }
@@ -103,8 +114,10 @@ extern "C" void restriction(level_type *level_c, int id_c, level_type *level_f, 
   } else
     run_restriction_list(level_c, id_c, level_f, id_f, local, restrictionType);                                 /* local */
   if (remote) {
-    hpgmg_comm_transfer_wait(level_f, Cf, level_c, Cc);
+    if (p2p_recv) hpgmg_comm_xfer_wait(Cc);
+    else if (!p2p) hpgmg_comm_transfer_wait(level_f, Cf, level_c, Cc);
     hpgmg_run_copy_list(Dc->L, id_c, Dc->restriction[restrictionType][2]);                                      /* unpack */
+    if (p2p_recv) hpgmg_comm_xfer_ack(Cc);
   }
 }
 
@@ -126,62 +139,69 @@ __device__ __forceinline__ void prolong5(const double cmm, const double cm, cons
   hi = (c0 - c1 * (cm - cp) - c2 * (cmm - cpp));
 }
 
-template <int W>   /* W = 3 (v2) or 5 (v4): stencil width per axis */
-__global__ void __launch_bounds__(128) interpolation_kernel(const DLevel Lf, const int id_f, const double prescale,
-                                                            const DLevel Lc, const int id_c,
-                                                            const blockCopy_type *__restrict__ blocks, const int force_zero_prescale)
+/* box -> MESSAGE entries (the fine boxes belong to another rank, mg.c:246-270), W = 3 (v2) or 5 (v4): the message is dense
+ * [k][j][i] at fine resolution.  The reference interpolates "in place" into its send buffer with prescale 0.0, i.e. it
+ * computes 0.0*old + value (blockCopy.c:153 remark) -- old being what the buffer held from the previous message.  With peer
+ * memory the message is written straight into the RECEIVER's buffer; reading `old` from there would be an NVLink round trip
+ * per cell, so the rank's own send buffer is kept as a mirror: old is read from it, the value goes to both.  Fine i-pairs
+ * leave as 16-byte stores (the 8-byte stores of the generic kernel reached the peer half-empty: 80 us per message). */
+template <int W>
+__global__ void __launch_bounds__(128) interpolation_pack_kernel(const DLevel Lc, const int id_c, const blockCopy_type *__restrict__ blocks,
+                                                                 const blockCopy_type *__restrict__ mirror_blocks)
 {
   PDL_WAIT();
   constexpr int R = W / 2;
   const blockCopy_type B = blocks[blockIdx.x];
-  const double *__restrict__ rd;
-  double *__restrict__ wr;
-  int rj, rk, wj, wk;
-  if (B.read.box >= 0) { rd = Lc.vec(B.read.box, id_c); rj = Lc.jStride; rk = Lc.kStride; }
-  else                 { rd = B.read.ptr;               rj = B.read.jStride; rk = B.read.kStride; }
-  if (B.write.box >= 0) { wr = Lf.vec(B.write.box, id_f); wj = Lf.jStride; wk = Lf.kStride; }
-  else                  { wr = B.write.ptr;               wj = B.write.jStride; wk = B.write.kStride; }
-  const double ps = force_zero_prescale ? 0.0 : prescale;
+  const int rj = Lc.jStride, rk = Lc.kStride, wj = B.write.jStride, wk = B.write.kStride;
+  const double *__restrict__ rd = Lc.vec(B.read.box, id_c);
+  double *__restrict__ wr = B.write.ptr;
+  double *__restrict__ mr = mirror_blocks ? mirror_blocks[blockIdx.x].write.ptr : B.write.ptr;       /* where `old` lives */
+  const bool twice = mirror_blocks != nullptr;
   const int di = B.dim.i, dj = B.dim.j, cells = di * dj * B.dim.k;
   for (int c = threadIdx.x; c < cells; c += blockDim.x) {
     const int ii = c % di, jj = (c / di) % dj, kk = c / (di * dj);
     const double *r = rd + (ii + B.read.i) + (jj + B.read.j) * rj + (kk + B.read.k) * rk;
-    /* pass 1: along i  -> fi[2][W][W]   (fine i, coarse j, coarse k) */
-    double fi[2][W][W];
-#pragma unroll
-    for (int K = 0; K < W; K++)
-#pragma unroll
-    for (int J = 0; J < W; J++) {
-      const double *p = r + (J - R) * rj + (K - R) * rk;
-      if constexpr (W == 3) prolong3(p[-1], p[0], p[1], fi[0][J][K], fi[1][J][K]);
-      else        prolong5(p[-2], p[-1], p[0], p[1], p[2], fi[0][J][K], fi[1][J][K]);
-    }
-    /* pass 2: along j  -> fj[2][2][W]   (fine i, fine j, coarse k) */
     double fj[2][2][W];
 #pragma unroll
-    for (int K = 0; K < W; K++)
+    for (int K = 0; K < W; K++) {
+      double fi[2][W];
 #pragma unroll
-    for (int I = 0; I < 2; I++) {
-      if constexpr (W == 3) prolong3(fi[I][0][K], fi[I][1][K], fi[I][2][K], fj[I][0][K], fj[I][1][K]);
-      else        prolong5(fi[I][0][K], fi[I][1][K], fi[I][2][K], fi[I][3][K], fi[I][W - 1][K], fj[I][0][K], fj[I][1][K]);
+      for (int J = 0; J < W; J++) {
+        const double *p = r + (J - R) * rj + (K - R) * rk;
+        if constexpr (W == 3) prolong3(p[-1], p[0], p[1], fi[0][J], fi[1][J]);
+        else                  prolong5(p[-2], p[-1], p[0], p[1], p[2], fi[0][J], fi[1][J]);
+      }
+#pragma unroll
+      for (int I = 0; I < 2; I++) {
+        if constexpr (W == 3) prolong3(fi[I][0], fi[I][1], fi[I][2], fj[I][0][K], fj[I][1][K]);
+        else                  prolong5(fi[I][0], fi[I][1], fi[I][2], fi[I][3], fi[I][W - 1], fj[I][0][K], fj[I][1][K]);
+      }
     }
-    /* pass 3: along k and commit */
-    double *w = wr + (2 * ii + B.write.i) + (2 * jj + B.write.j) * wj + (2 * kk + B.write.k) * wk;
+    const int off = (2 * ii + B.write.i) + (2 * jj + B.write.j) * wj + (2 * kk + B.write.k) * wk;
+    const bool vec2 = ((off & 1) == 0) && ((reinterpret_cast<uintptr_t>(wr) & 15) == 0) && ((reinterpret_cast<uintptr_t>(mr) & 15) == 0) && ((wj & 1) == 0) && ((wk & 1) == 0);
 #pragma unroll
-    for (int J = 0; J < 2; J++)
+    for (int J = 0; J < 2; J++) {
+      double lo[2], hi[2];
 #pragma unroll
-    for (int I = 0; I < 2; I++) {
-      double lo, hi;
-      if constexpr (W == 3) prolong3(fj[I][J][0], fj[I][J][1], fj[I][J][2], lo, hi);
-      else        prolong5(fj[I][J][0], fj[I][J][1], fj[I][J][2], fj[I][J][3], fj[I][J][W - 1], lo, hi);
-      double *w0 = w + I + J * wj;
-      w0[0]  = ps * w0[0] + lo;
-      w0[wk] = ps * w0[wk] + hi;
+      for (int I = 0; I < 2; I++) {
+        if constexpr (W == 3) prolong3(fj[I][J][0], fj[I][J][1], fj[I][J][2], lo[I], hi[I]);
+        else                  prolong5(fj[I][J][0], fj[I][J][1], fj[I][J][2], fj[I][J][3], fj[I][J][W - 1], lo[I], hi[I]);
+      }
+      const int o = off + J * wj;
+      const double a0 = 0.0 * mr[o] + lo[0], a1 = 0.0 * mr[o + 1] + lo[1], b0 = 0.0 * mr[o + wk] + hi[0], b1 = 0.0 * mr[o + wk + 1] + hi[1];
+      if (vec2) {
+        *reinterpret_cast<double2 *>(wr + o) = make_double2(a0, a1);
+        *reinterpret_cast<double2 *>(wr + o + wk) = make_double2(b0, b1);
+        if (twice) { *reinterpret_cast<double2 *>(mr + o) = make_double2(a0, a1); *reinterpret_cast<double2 *>(mr + o + wk) = make_double2(b0, b1); }
+      } else {
+        wr[o] = a0;  wr[o + 1] = a1;  wr[o + wk] = b0;  wr[o + wk + 1] = b1;
+        if (twice) { mr[o] = a0;  mr[o + 1] = a1;  mr[o + wk] = b0;  mr[o + wk + 1] = b1; }
+      }
     }
   }
 }
 
-/* The same arithmetic for box -> box entries, staged through shared memory: a thread block takes a
+/* box -> box entries, staged through shared memory: a thread block takes a
  * 32 x 4 x 2 sub-tile of coarse cells of one list entry, loads the tile plus its W/2-cell halo once
  * (instead of every thread fetching 27 / 125 overlapping values through L1), and writes each fine
  * i-pair as one 16-byte access. */
@@ -352,9 +372,19 @@ static void interpolation_driver(level_type *level_f, int id_f, double prescale_
   hpgmg_device_level *Df = HPGMG_DEV(level_f), *Dc = HPGMG_DEV(level_c);
   communicator_type *Cc = &level_c->interpolation, *Cf = &level_f->interpolation;
   const int remote = (Cc->num_sends > 0) || (Cf->num_recvs > 0);
-  if (remote) {
+  DList peer_pack = { NULL, 0 };
+  const int p2p_send = Cc->num_sends > 0 && hpgmg_comm_xfer_send_lookup(Cc, (const blockCopy_type **)&peer_pack.blocks, &peer_pack.n);
+  const int p2p_recv = Cf->num_recvs > 0 && hpgmg_comm_xfer_recv_lookup(Cf);
+  const int p2p = p2p_send || p2p_recv;
+  if (remote && p2p) {
+    if (p2p_send) {                                                  /* interpolate straight into the fine boxes' owners (comm.cu) */
+      hpgmg_comm_xfer_pre(Cc);
+      if (peer_pack.n > 0) LAUNCH(interpolation_pack_kernel<W>, peer_pack.n, 128, 0, Dc->L, id_c, peer_pack.blocks, Dc->interpolation[0].blocks);
+      hpgmg_comm_xfer_post(Cc);
+    }
+  } else if (remote) {
     const DList &pack = Dc->interpolation[0];
-    if (pack.n > 0) LAUNCH(interpolation_kernel<W>, pack.n, 128, 0, Df->L, id_f, 0.0, Dc->L, id_c, pack.blocks, 1);
+    if (pack.n > 0) LAUNCH(interpolation_pack_kernel<W>, pack.n, 128, 0, Dc->L, id_c, pack.blocks, (const blockCopy_type *)NULL);
     hpgmg_comm_transfer(level_c, Cc, level_f, Cf, 0x7);
   }
   const DList &local = Dc->interpolation[1];
@@ -371,9 +401,11 @@ static void interpolation_driver(level_type *level_f, int id_f, double prescale_
       LAUNCH(interpolation_tiled_kernel<W>, dim3(local.n, subtiles), dim3(32, 4, 2), 0, Df->L, id_f, prescale_f, Dc->L, id_c, local.blocks);
   }
   if (remote) {
-    hpgmg_comm_transfer_wait(level_c, Cc, level_f, Cf);
+    if (p2p_recv) hpgmg_comm_xfer_wait(Cf);
+    else if (!p2p) hpgmg_comm_transfer_wait(level_c, Cc, level_f, Cf);
     const DList &unpack = Df->interpolation[2];
     if (unpack.n > 0) LAUNCH(increment_blocks_kernel, unpack.n, 128, 0, Df->L, id_f, prescale_f, unpack.blocks);
+    if (p2p_recv) hpgmg_comm_xfer_ack(Cf);
   }
 }
 

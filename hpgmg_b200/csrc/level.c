@@ -479,6 +479,7 @@ void create_level(level_type *L, int boxes_in_i, int box_dim, int box_ghosts, in
     exit(0);
   }
 
+  hpgmg_comm_recycle_arena();      /* collective: peer-visible buffers of destroyed hierarchies are handed out again */
   memset(L, 0, sizeof(*L));
   L->box_dim = box_dim;           L->box_ghosts = box_ghosts;
   L->boxes_in.i = L->boxes_in.j = L->boxes_in.k = boxes_in_i;

@@ -183,7 +183,7 @@ static void build_restriction(mg_type *MG, int type)
       C->num_recvs = nRanks;
       if (nRanks > 0) {
         alloc_neighbours(nRanks, &C->recv_ranks, &C->recv_sizes, &C->recv_buffers);
-        double *bulk = (double *)MALLOC((size_t)nRemote * elem * sizeof(double));
+        double *bulk = (double *)hpgmg_rt_alloc_comm((size_t)nRemote * elem * sizeof(double));      /* peer-visible: senders store straight into it */
         for (int r = 0; r < nRanks; r++) {
           int offset = 0;
           C->recv_buffers[r] = bulk;
@@ -305,7 +305,7 @@ static void build_interpolation(mg_type *MG)
       C->num_recvs = nRanks;
       if (nRanks > 0) {
         alloc_neighbours(nRanks, &C->recv_ranks, &C->recv_sizes, &C->recv_buffers);
-        double *bulk = (double *)MALLOC((size_t)nRemote * elem * sizeof(double));
+        double *bulk = (double *)hpgmg_rt_alloc_comm((size_t)nRemote * elem * sizeof(double));      /* peer-visible: senders store straight into it */
         for (int r = 0; r < nRanks; r++) {
           int offset = 0;
           C->recv_buffers[r] = bulk;
@@ -361,6 +361,25 @@ static int next_level_spec(const level_spec *f, int odd, int radius, level_spec 
   return 1;
 }
 
+/* Ownership agglomeration (multi-GPU only).  The reference keeps a level spread over all ranks until its boxes merge
+ * (rule 2) -- fine for CPUs, where a coarse-level ghost exchange costs a microsecond.  Between GPUs every exchange of a
+ * level that is all latency costs an NVLink round trip, ~300 times per solve.  So levels whose boxes have at most
+ * `g_agglomerate_box` cells per side, or that are at most 4 times that wide in total (64^3 cells: one GPU runs such a
+ * level faster than several can exchange its halos), and every coarser level are OWNED by rank 0: the box structure -- and therefore
+ * every bit of the result -- is unchanged, only rank_of_box differs; the transfers into and out of such a level are the
+ * all-to-one / one-to-all messages the reference's own rank-shrinking rules (mg.c:918-941) already produce.
+ * 0 reproduces the reference's decomposition exactly. */
+static int g_agglomerate_box = -1;
+void hpgmg_b200_set_agglomeration(int box_dim) { g_agglomerate_box = box_dim < 0 ? 0 : box_dim; }
+int  hpgmg_b200_get_agglomeration(void)
+{
+  if (g_agglomerate_box < 0) {
+    const char *e = getenv("HPGMG_B200_AGGLOMERATE_BOX");
+    g_agglomerate_box = e ? atoi(e) : 16;
+  }
+  return g_agglomerate_box;
+}
+
 void MGBuild(mg_type *MG, level_type *fine, double a, double b, int minCoarseGridDim)
 {
   const double t0 = hpgmg_rt_wtime();
@@ -386,6 +405,8 @@ void MGBuild(mg_type *MG, level_type *fine, double a, double b, int minCoarseGri
     int l = MG->num_levels;
     if (!next_level_spec(&spec[l - 1], odd, stencil_get_radius(), &spec[l])) break;
     if (spec[l].dim < minCoarseGridDim) break;
+    if (spec[l].nProcs > 1 && hpgmg_b200_get_agglomeration() > 0 &&
+        (spec[l].box_dim <= hpgmg_b200_get_agglomeration() || spec[l].dim <= 4 * hpgmg_b200_get_agglomeration())) spec[l].nProcs = 1;   /* owned by rank 0 from here down */
     MG->num_levels++;
   }
 
@@ -406,6 +427,11 @@ void MGBuild(mg_type *MG, level_type *fine, double a, double b, int minCoarseGri
   build_restriction(MG, RESTRICT_FACE_K);
   build_interpolation(MG);
   for (int l = 0; l < MG->num_levels; l++) hpgmg_device_level_upload_transfer_lists(MG->levels[l]);
+  /* collective: swap buffer / flag addresses of every inter-level message (comm.cu) */
+  for (int l = 0; l + 1 < MG->num_levels; l++) {
+    for (int t = 0; t < 4; t++) hpgmg_comm_register_transfer(&MG->levels[l]->restriction[t], &MG->levels[l + 1]->restriction[t]);
+    hpgmg_comm_register_transfer(&MG->levels[l + 1]->interpolation, &MG->levels[l]->interpolation);
+  }
   if (chatty) { fprintf(stdout, "done\n"); fflush(stdout); }
 
   /* a rank is active on level l if it owns boxes there or on any coarser level (mg.c:985-986).
@@ -441,8 +467,9 @@ void MGDestroy(mg_type *MG)
   hpgmg_forget_norms(MG);
   if (chatty) { fprintf(stdout, "attempting to free the restriction and interpolation lists... "); fflush(stdout); }
   for (int l = MG->num_levels - 1; l >= 0; l--) {
+    hpgmg_comm_unregister_transfer(&MG->levels[l]->interpolation);
     hpgmg_free_communicator(&MG->levels[l]->interpolation);
-    for (int t = 3; t >= 0; t--) hpgmg_free_communicator(&MG->levels[l]->restriction[t]);
+    for (int t = 3; t >= 0; t--) { hpgmg_comm_unregister_transfer(&MG->levels[l]->restriction[t]); hpgmg_free_communicator(&MG->levels[l]->restriction[t]); }
   }
   if (chatty) fprintf(stdout, "done\n");
   for (int l = MG->num_levels - 1; l > 0; l--) {       /* level 0 belongs to the caller */

@@ -76,8 +76,18 @@ void hpgmg_rt_zero_scalar(int slot);                  /* async, capturable */
 /* peer-visible device memory for receive buffers and flags (comm.cu); plain device memory on one rank */
 void  *hpgmg_rt_alloc_comm(size_t bytes);
 int    hpgmg_rt_is_comm_memory(const void *p);
+void   hpgmg_rt_free_comm(void *p);
+void   hpgmg_comm_recycle_arena(void);                              /* collective; start of create_level */
 void   hpgmg_comm_register_exchange(level_type *level, int shape);   /* collective over all ranks */
 void   hpgmg_comm_unregister(communicator_type *C);
+void   hpgmg_comm_register_transfer(communicator_type *Cs, communicator_type *Cr);   /* collective; MGBuild */
+void   hpgmg_comm_unregister_transfer(communicator_type *C);
+int    hpgmg_comm_xfer_send_lookup(communicator_type *Cs, const blockCopy_type **pack, int *npack);
+int    hpgmg_comm_xfer_recv_lookup(communicator_type *Cr);
+void   hpgmg_comm_xfer_pre(communicator_type *Cs);
+void   hpgmg_comm_xfer_post(communicator_type *Cs);
+void   hpgmg_comm_xfer_wait(communicator_type *Cr);
+void   hpgmg_comm_xfer_ack(communicator_type *Cr);
 
 /* inter-GPU plumbing (comm.cu): no-ops on a single rank */
 int    hpgmg_comm_rank(void);

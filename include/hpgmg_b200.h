@@ -123,6 +123,10 @@ typedef void (*hpgmg_allgather_fn)(const void *send, void *recv, size_t bytes_pe
 typedef void (*hpgmg_barrier_fn)(void *ctx);
 void hpgmg_b200_set_comm(int my_rank, int num_ranks, hpgmg_allgather_fn allgather, hpgmg_barrier_fn barrier, void *ctx);
 void hpgmg_b200_comm_finalize(void);
+/* Multi-GPU only: levels whose boxes have at most `box_dim` cells per side or that are at most 4*box_dim cells wide, and all
+ * coarser ones, are owned by rank 0 (default 16, i.e. boxes <= 16^3 or levels <= 64^3; 0 = exactly the reference's rank_of_box).  Same boxes, same bits; call before MGBuild on every rank. */
+void hpgmg_b200_set_agglomeration(int box_dim);
+int  hpgmg_b200_get_agglomeration(void);
 /* 1 if ghost exchanges go through direct peer stores (CUDA IPC over NVLink), 0 if through ncclSend/ncclRecv */
 int  hpgmg_b200_p2p_enabled(void);
 

@@ -18,29 +18,39 @@ import oracle_bindings as ob
 dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 L = api.lib(); L.hpgmg_b200_set_layout_only(1); L.hpgmg_b200_set_verbose(0)
-H = api.Hierarchy(5, 8, my_rank=rank, num_ranks=world, build_operator=False)
-L.MGBuild(H.mg, H.level_h, 0.0, 1.0, 1); H.built = True
-mine = [ob.level_list_summary(H.level(l)) for l in range(H.num_levels)]
-everyone = [None] * world
-dist.all_gather_object(everyone, mine)
-gold = ob.goldens()["decompositions"]["5 8 x%d" % world]
-assert mine == gold[rank], "lists differ from the reference for rank %d" % rank
-def table(summary, kind):
-    return summary[kind] if kind == "interpolation" else None
-bad = []
-for l in range(len(mine)):
-    comms = [("exchange", s) for s in range(3)] + [("restriction", t) for t in range(4)] + [("interpolation", None)]
-    for kind, idx in comms:
-        get = lambda r, lev: everyone[r][lev][kind] if idx is None else everyone[r][lev][kind][idx]
-        # sender side of level l talks to: the same level (exchange), level l+1 (restriction), level l-1 (interpolation)
-        lr = l if kind == "exchange" else (l + 1 if kind == "restriction" else l - 1)
-        if lr < 0 or lr >= len(mine):
-            continue
-        for dst, size in get(rank, l)["send"]:
-            expect = dict(get(dst, lr)["recv"]).get(rank)
-            if expect != size:
-                bad.append((kind, idx, l, rank, dst, size, expect))
-assert not bad, bad
+for agglomerate in (0, 16):
+  L.hpgmg_b200_set_agglomeration(agglomerate)
+  H = api.Hierarchy(5, 8, my_rank=rank, num_ranks=world, build_operator=False)
+  L.MGBuild(H.mg, H.level_h, 0.0, 1.0, 1); H.built = True
+  mine = [ob.level_list_summary(H.level(l)) for l in range(H.num_levels)]
+  everyone = [None] * world
+  dist.all_gather_object(everyone, mine)
+  gold = ob.goldens()["decompositions"]["5 8 x%d" % world]
+  if agglomerate == 0:
+    assert mine == gold[rank], "lists differ from the reference for rank %d" % rank
+  else:
+    # ownership agglomeration: same boxes on every level, levels with boxes <= 16^3 entirely on rank 0
+    for lv, g in zip(mine, gold[rank]):
+      assert (lv["dim"], lv["box_dim"], lv["boxes_in"]) == (g["dim"], g["box_dim"], g["boxes_in"])
+      if lv["box_dim"] <= 16:
+        assert set(lv["rank_of_box"]) == {0} and lv["num_my_boxes"] == (len(lv["rank_of_box"]) if rank == 0 else 0)
+      else:
+        assert lv["rank_of_box"] == g["rank_of_box"]
+  bad = []
+  for l in range(len(mine)):
+      comms = [("exchange", s) for s in range(3)] + [("restriction", t) for t in range(4)] + [("interpolation", None)]
+      for kind, idx in comms:
+          get = lambda r, lev: everyone[r][lev][kind] if idx is None else everyone[r][lev][kind][idx]
+          # sender side of level l talks to: the same level (exchange), level l+1 (restriction), level l-1 (interpolation)
+          lr = l if kind == "exchange" else (l + 1 if kind == "restriction" else l - 1)
+          if lr < 0 or lr >= len(mine):
+              continue
+          for dst, size in get(rank, l)["send"]:
+              expect = dict(get(dst, lr)["recv"]).get(rank)
+              if expect != size:
+                  bad.append((kind, idx, l, rank, dst, size, expect))
+  assert not bad, bad
+  H.close()
 total_boxes = torch.tensor([sum(1 for r in mine[0]["rank_of_box"] if r == rank)])
 dist.all_reduce(total_boxes)
 assert int(total_boxes) == len(mine[0]["rank_of_box"])

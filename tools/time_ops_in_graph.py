@@ -6,13 +6,13 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import hpgmg_b200.api as api
 
-api.init(0)
+rank, world = api.init_distributed()          # plain `python` (1 GPU) or under torchrun
 L = api.lib()
 L.hpgmg_graph_begin.restype = C.c_int
 L.hpgmg_graph_begin.argtypes = [C.c_void_p, C.c_longlong]
 L.hpgmg_graph_end.argtypes = [C.c_void_p, C.c_longlong]
 log2 = int(sys.argv[1]) if len(sys.argv) > 1 else 7
-H = api.Hierarchy(log2, 8, use_graphs=True)
+H = api.Hierarchy(log2, 8, my_rank=rank, num_ranks=world, use_graphs=True)
 H.fmg_solve(0)
 U, R, T, E = api.VECTOR_U, api.VECTOR_R, api.VECTOR_TEMP, api.VECTOR_E
 key = [1000]
@@ -34,7 +34,7 @@ def timed(fn, K=20, reps=5):
     return 1e3 * L.hpgmg_b200_bench_elapsed_ms(0, 1) / (K * reps)
 
 
-for l in range(0, H.num_levels - 1):
+for l in range(0, min(H.num_levels - 1, 4 if world > 1 else 99)):
     lv = H.level(l)
     lc = H.level(l + 1)
     c = lv.contents
@@ -48,5 +48,10 @@ for l in range(0, H.num_levels - 1):
         "interp_v4": timed(lambda: L.interpolation_fcycle(lv, U, 0.0, lc, U)),
         "vcycle": timed(lambda: L.MGVCycle(H.mg, U, R, 0.0, 1.0, l), K=4),
     }
-    print(f"level {l} dim {c.dim.i} box {c.box_dim}: " + "  ".join(f"{k} {v:.1f}" for k, v in row.items()), flush=True)
+    if rank == 0:
+        print(f"world {world} level {l} dim {c.dim.i} box {c.box_dim} boxes {c.num_my_boxes} ranks {c.num_ranks}: " + "  ".join(f"{k} {v:.1f}" for k, v in row.items()), flush=True)
 H.close()
+if world > 1:
+    import torch.distributed as dist
+    L.hpgmg_b200_comm_finalize()
+    dist.destroy_process_group()
