@@ -49,6 +49,8 @@ SIGNATURES = {
     "hpgmg_b200_host_alloc_pinned": (C.c_void_p, [C.c_size_t]), "hpgmg_b200_host_free_pinned": (_V, [C.c_void_p]),
     "hpgmg_fmg_solve_host": (_D, [_MP, _I, _I, _I, _D, _D, _D, C.c_void_p, C.c_void_p]),
     "hpgmg_fmg_solve_host_bytes": (C.c_ulonglong, [_MP, _I]),
+    "hpgmg_fmg_solve_host_submit": (_I, [_MP, _I, _I, _I, _D, _D, _D, C.c_void_p, C.c_void_p]),
+    "hpgmg_fmg_solve_host_wait": (_D, [_MP, _I]),
     "hpgmg_last_norm_of_F": (_D, [_MP]), "hpgmg_last_norm_of_residual": (_D, [_MP]),
     "hpgmg_last_richardson_error": (_D, []), "hpgmg_last_richardson_order": (_D, []),
     "hpgmg_b200_kernel_launches": (C.c_ulonglong, []), "hpgmg_b200_device_seconds_last_solve": (_D, []),
@@ -176,7 +178,8 @@ class Hierarchy:
     """
 
     def __init__(self, log2_box_dim, target_boxes_per_rank, my_rank=0, num_ranks=1, a=0.0, b=1.0,
-                 smoother=SMOOTHER_GSRB, verbose=False, use_graphs=True, build_operator=True, library=None):
+                 smoother=SMOOTHER_GSRB, verbose=False, use_graphs=True, build_operator=True, library=None,
+                 bc=BC_DIRICHLET, vectors=None):
         self.L = library or lib()
         self.a, self.b = float(a), float(b)
         self.box_dim, self.boxes_in_i = problem_size(log2_box_dim, target_boxes_per_rank, num_ranks)
@@ -188,8 +191,9 @@ class Hierarchy:
             self.L.hpgmg_b200_use_graphs(1 if use_graphs else 0)
         self._level_buf = level_type()
         self.level_h = C.pointer(self._level_buf)
+        self.bc = bc
         self.L.create_level(self.level_h, self.boxes_in_i, self.box_dim, self.L.stencil_get_radius(),
-                            VECTORS_RESERVED, BC_DIRICHLET, my_rank, num_ranks)
+                            VECTORS_RESERVED if vectors is None else vectors, bc, my_rank, num_ranks)
         self.h = 1.0 / (float(self.boxes_in_i) * float(self.box_dim))
         self._mg_buf = mg_type()
         self.mg = C.pointer(self._mg_buf)
@@ -197,7 +201,11 @@ class Hierarchy:
         if build_operator:
             self.L.initialize_problem(self.level_h, self.h, self.a, self.b)
             self.L.rebuild_operator(self.level_h, None, self.a, self.b)
-            self.L.MGBuild(self.mg, self.level_h, self.a, self.b, 1)
+            if bc == BC_PERIODIC:                  # remove any constant from the RHS (hpgmg-fv.c:296-302)
+                average = self.L.mean(self.level_h, VECTOR_F)
+                if average != 0.0:
+                    self.L.shift_vector(self.level_h, VECTOR_F, VECTOR_F, -average)
+            self.L.MGBuild(self.mg, self.level_h, self.a, self.b, 2 if bc == BC_PERIODIC else 1)   # hpgmg-fv.c:278,281
             self.built = True
 
     # -- accessors -------------------------------------------------------------------------------

@@ -36,8 +36,9 @@ static double *g_scalars = NULL;            /* device, HPGMG_NUM_SCALARS doubles
 static double *g_scalars_host = NULL;       /* pinned mirror                      */
 static cudaEvent_t g_ev0, g_ev1;
 static double g_last_device_seconds = 0.0;
-static void *g_staging[2] = { NULL, NULL };     /* dense cells of f / u of the end-to-end solve */
-static size_t g_staging_bytes[2] = { 0, 0 };
+#define NSTAGING 4                                /* dense cells of f / u of the end-to-end solve: [0],[1] slot 0; [2],[3] slot 1 */
+static void *g_staging[NSTAGING] = { NULL, NULL, NULL, NULL };
+static size_t g_staging_bytes[NSTAGING] = { 0, 0, 0, 0 };
 static cudaStream_t g_side_stream = 0, g_main_stream_saved = 0;
 static cudaEvent_t g_ev_fork = 0, g_ev_join = 0;
 
@@ -114,7 +115,8 @@ extern "C" void hpgmg_b200_finalize(void)
   cudaStreamSynchronize(g_stream);
   hpgmg_graph_drop_all(NULL);
   cudaFree(g_scalars);  cudaFreeHost(g_scalars_host);
-  for (int w = 0; w < 2; w++) { if (g_staging[w]) cudaFree(g_staging[w]); g_staging[w] = NULL; g_staging_bytes[w] = 0; }
+  for (int w = 0; w < NSTAGING; w++) { if (g_staging[w]) cudaFree(g_staging[w]); g_staging[w] = NULL; g_staging_bytes[w] = 0; }
+  hpgmg_rt_pipe_destroy();
   if (g_side_stream) { cudaStreamDestroy(g_side_stream); cudaEventDestroy(g_ev_fork); cudaEventDestroy(g_ev_join); g_side_stream = 0; }
   cudaEventDestroy(g_ev0);  cudaEventDestroy(g_ev1);
   cudaStreamDestroy(g_stream);
@@ -353,3 +355,74 @@ extern "C" void hpgmg_rt_side_end(void)
 }
 /* the compute stream waits for the side work */
 extern "C" void hpgmg_rt_side_join(void) { CUDA_CHECK(cudaStreamWaitEvent(g_stream, g_ev_join, 0)); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* Pipelined end-to-end solves (hpgmg_fmg_solve_host_submit / _wait, mg.c): two slots, each with its own staging buffers.
+ * The upload of solve n+1 runs on its own stream while solve n computes, the download of solve n while solve n+1 computes
+ * (PCIe is full duplex); the compute stream only ever waits for "f of this slot has arrived".  A slot is reused only after
+ * the host has waited for its previous solve, so its staging buffers are free by then. */
+static cudaStream_t g_up_stream = 0, g_down_stream = 0;
+static cudaEvent_t g_ev_up[2], g_ev_packed[2], g_ev_down[2], g_ev_scal[2];
+static double *g_pipe_scalars_host = NULL;            /* pinned, 2 x 4 doubles */
+static void pipe_init(void)
+{
+  if (g_up_stream) return;
+  CUDA_CHECK(cudaStreamCreateWithFlags(&g_up_stream, cudaStreamNonBlocking));
+  CUDA_CHECK(cudaStreamCreateWithFlags(&g_down_stream, cudaStreamNonBlocking));
+  for (int s = 0; s < 2; s++) {
+    CUDA_CHECK(cudaEventCreateWithFlags(&g_ev_up[s], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&g_ev_packed[s], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&g_ev_down[s], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&g_ev_scal[s], cudaEventDisableTiming));
+  }
+  CUDA_CHECK(cudaHostAlloc(&g_pipe_scalars_host, 8 * sizeof(double), cudaHostAllocMapped));
+}
+/* three doubles straight into mapped host memory: a D2H copy here would queue behind the 134 MB download of this very
+ * solve on the copy engine and hold the compute stream (and with it the next solve) for its 2.5 ms */
+__global__ void publish_scalars_kernel(double *host_mapped, const double *src)
+{
+  PDL_WAIT();
+  if (threadIdx.x < 3) host_mapped[threadIdx.x] = src[threadIdx.x];
+  __threadfence_system();
+}
+extern "C" void hpgmg_rt_pipe_destroy(void)
+{
+  if (!g_up_stream) return;
+  cudaStreamSynchronize(g_up_stream);  cudaStreamSynchronize(g_down_stream);
+  for (int s = 0; s < 2; s++) { cudaEventDestroy(g_ev_up[s]); cudaEventDestroy(g_ev_packed[s]); cudaEventDestroy(g_ev_down[s]); cudaEventDestroy(g_ev_scal[s]); }
+  cudaStreamDestroy(g_up_stream);  cudaStreamDestroy(g_down_stream);
+  cudaFreeHost(g_pipe_scalars_host);
+  g_up_stream = g_down_stream = 0;  g_pipe_scalars_host = NULL;
+}
+/* f_host -> stage on the upload stream; the compute stream waits for it (and for nothing else) */
+extern "C" void hpgmg_rt_pipe_upload(int slot, void *stage, const void *host, size_t bytes)
+{
+  pipe_init();
+  if (bytes) CUDA_CHECK(cudaMemcpyAsync(stage, host, bytes, cudaMemcpyHostToDevice, g_up_stream));
+  CUDA_CHECK(cudaEventRecord(g_ev_up[slot], g_up_stream));
+  CUDA_CHECK(cudaStreamWaitEvent(g_stream, g_ev_up[slot], 0));
+}
+/* u has been packed into `stage` by everything enqueued so far on the compute stream: send it home on the download stream */
+extern "C" void hpgmg_rt_pipe_download(int slot, void *host, const void *stage, size_t bytes)
+{
+  pipe_init();
+  CUDA_CHECK(cudaEventRecord(g_ev_packed[slot], g_stream));
+  CUDA_CHECK(cudaStreamWaitEvent(g_down_stream, g_ev_packed[slot], 0));
+  if (bytes) CUDA_CHECK(cudaMemcpyAsync(host, stage, bytes, cudaMemcpyDeviceToHost, g_down_stream));
+  CUDA_CHECK(cudaEventRecord(g_ev_down[slot], g_down_stream));
+}
+/* the solve's scalars (||F||, ||r||, Krylov iterations) as they are at this point of the compute stream */
+extern "C" void hpgmg_rt_pipe_scalars(int slot)
+{
+  pipe_init();
+  double *mapped = NULL;
+  CUDA_CHECK(cudaHostGetDevicePointer(&mapped, g_pipe_scalars_host + 4 * slot, 0));
+  LAUNCH(publish_scalars_kernel, 1, 32, 0, mapped, g_scalars + HPGMG_SLOT_NORM_F);
+  CUDA_CHECK(cudaEventRecord(g_ev_scal[slot], g_stream));
+}
+extern "C" void hpgmg_rt_pipe_wait(int slot, double *scalars3)
+{
+  CUDA_CHECK(cudaEventSynchronize(g_ev_scal[slot]));
+  CUDA_CHECK(cudaEventSynchronize(g_ev_down[slot]));
+  memcpy(scalars3, g_pipe_scalars_host + 4 * slot, 3 * sizeof(double));
+}

@@ -757,6 +757,73 @@ double hpgmg_fmg_solve_host(mg_type *MG, int onLevel, int u_id, int F_id, double
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* The same end-to-end solve, PIPELINED for back-to-back solves: submit() enqueues upload, solve and download of one solve
+ * and returns at once; wait() blocks until that solve's u_host and norms are complete.  Two solves may be in flight: while
+ * solve n computes, f of solve n+1 travels up and u of solve n-1 travels down on their own streams (PCIe is full duplex),
+ * so a stream of solves runs at max(compute, upload, download) per solve instead of their sum.  Each slot owns its staging
+ * buffers; the caller must not touch f_host / u_host of a submitted solve before wait() returns, and submits at most two
+ * solves before waiting for the older one.  Results are bit-identical to hpgmg_fmg_solve_host. */
+typedef struct { mg_type *MG; int onLevel, busy; } pipe_slot;
+static pipe_slot g_pipe[2];
+static int g_pipe_next = 0;
+int hpgmg_fmg_solve_host_submit(mg_type *MG, int onLevel, int u_id, int F_id, double a, double b, double rtol, const double *f_host, double *u_host)
+{
+  (void)rtol;
+  level_type *L = MG->levels[onLevel];
+  const size_t bytes = (size_t)hpgmg_fmg_solve_host_bytes(MG, onLevel);
+  if ((L->box_dim & 1) || !L->active) {
+    fprintf(stderr, "hpgmg_fmg_solve_host_submit: needs an even box size and an active level\n");
+    exit(1);
+  }
+  const int slot = g_pipe_next;
+  if (g_pipe[slot].busy) {
+    fprintf(stderr, "hpgmg_fmg_solve_host_submit: two solves are already in flight; wait for ticket %d first\n", slot);
+    exit(1);
+  }
+  g_pipe_next ^= 1;
+  g_pipe[slot].MG = MG;  g_pipe[slot].onLevel = onLevel;  g_pipe[slot].busy = 1;
+  MG->MGSolves_performed++;
+  const int e_id = u_id, R_id = VECTOR_R;
+  double *stage_f = bytes ? (double *)hpgmg_rt_staging(2 * slot, bytes) : NULL;
+  double *stage_u = bytes ? (double *)hpgmg_rt_staging(2 * slot + 1, bytes) : NULL;
+  const int capturable = solve_is_capturable(MG, L);
+  hpgmg_rt_pipe_upload(slot, stage_f, f_host, bytes);                            /* upload stream; the compute stream waits for it */
+  const long long key = solve_key(8 + slot, onLevel, u_id, F_id, a, b);
+  if (!capturable || hpgmg_graph_begin(MG, key)) {
+    hpgmg_rt_zero_scalar(HPGMG_SLOT_KRYLOV);
+    zero_vector(L, u_id);                                                        /* hpgmg-fv.c:78 */
+    hpgmg_unpack_copy_norm_async(L, F_id, R_id, stage_f, HPGMG_SLOT_NORM_F);
+    enqueue_fcycle_after_rhs(MG, onLevel, e_id, R_id, a, b);
+    if (L->must_subtract_mean != 1) hpgmg_pack_async(L, u_id, stage_u);          /* u is final */
+    if (capturable) hpgmg_graph_end(MG, key);
+  }
+  if (L->must_subtract_mean == 1) {                                              /* periodic: the mean is removed from u first (mg.c:1317-1320) */
+    enqueue_residual_norm(L, e_id, F_id, a, b);
+    hpgmg_pack_async(L, u_id, stage_u);
+    hpgmg_rt_pipe_download(slot, u_host, stage_u, bytes);
+  } else {
+    hpgmg_rt_pipe_download(slot, u_host, stage_u, bytes);                        /* download stream ... */
+    enqueue_residual_norm(L, e_id, F_id, a, b);                                  /* ... while the residual and its norm are computed */
+  }
+  hpgmg_rt_pipe_scalars(slot);
+  count_vcycle_visits(MG, onLevel);
+  return slot;
+}
+double hpgmg_fmg_solve_host_wait(mg_type *MG, int ticket)
+{
+  if (ticket < 0 || ticket > 1 || !g_pipe[ticket].busy || g_pipe[ticket].MG != MG) {
+    fprintf(stderr, "hpgmg_fmg_solve_host_wait: ticket %d is not an outstanding solve of this hierarchy\n", ticket);
+    exit(1);
+  }
+  double s[3];
+  hpgmg_rt_pipe_wait(ticket, s);
+  g_pipe[ticket].busy = 0;
+  MG->levels[MG->num_levels - 1]->Krylov_iterations += (int)s[2];
+  record_norms(MG, s[0], s[1]);
+  return s[1];
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* V-cycles to convergence from a zero initial guess (mg.c:1168-1233). */
 void MGSolve(mg_type *MG, int onLevel, int u_id, int F_id, double a, double b, double rtol)
 {

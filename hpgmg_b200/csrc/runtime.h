@@ -112,6 +112,11 @@ void *hpgmg_rt_staging(int which, size_t bytes);
 void  hpgmg_rt_side_begin(void);
 void  hpgmg_rt_side_end(void);
 void  hpgmg_rt_side_join(void);
+void  hpgmg_rt_pipe_upload(int slot, void *stage, const void *host, size_t bytes);      /* pipelined solves: upload / download streams */
+void  hpgmg_rt_pipe_download(int slot, void *host, const void *stage, size_t bytes);
+void  hpgmg_rt_pipe_scalars(int slot);
+void  hpgmg_rt_pipe_wait(int slot, double *scalars3);
+void  hpgmg_rt_pipe_destroy(void);
 void  hpgmg_unpack_copy_norm_async(level_type *level, int id_f, int id_r, const double *dense, int slot);   /* F = dense; R = 1.0*F; slot = max|F| */
 void  hpgmg_pack_async(level_type *level, int id, double *dense);
 void  hpgmg_unpack_async(level_type *level, int id, const double *dense);

@@ -90,6 +90,14 @@ void  hpgmg_b200_host_free_pinned(void *p);
 double hpgmg_fmg_solve_host(mg_type *all_grids, int onLevel, int u_id, int F_id, double a, double b,
                             double rtol, const double *f_host, double *u_host);
 unsigned long long hpgmg_fmg_solve_host_bytes(mg_type *all_grids, int onLevel);
+/* The same call split in two for a stream of solves: submit() enqueues upload + solve + download and returns a ticket
+ * (0 or 1) at once, wait() blocks until that solve's u_host is complete and returns its residual norm.  Up to two solves
+ * may be in flight; the upload of the next and the download of the previous solve then overlap the running one, each on
+ * its own stream.  Same bits as hpgmg_fmg_solve_host.  f_host / u_host of a submitted solve belong to the library until
+ * wait() returns. */
+int    hpgmg_fmg_solve_host_submit(mg_type *all_grids, int onLevel, int u_id, int F_id, double a, double b,
+                                   double rtol, const double *f_host, double *u_host);
+double hpgmg_fmg_solve_host_wait(mg_type *all_grids, int ticket);
 
 /* Norms of the last FMGSolve/MGSolve on this hierarchy: ||F||, ||r|| after the F-cycle (or
  * last V-cycle).  The reference only prints them (mg.c:1325-1329); tests need the values. */

@@ -135,9 +135,10 @@ def quiet():
 class RefHierarchy:
     """hpgmg-fv.c:280-308 executed by the reference library on host memory."""
 
-    def __init__(self, log2_box_dim, target_boxes_per_rank, my_rank=0, num_ranks=1, cheby=False, build_operator=True):
-        self.L = ref(cheby)
-        self.a, self.b = 0.0, 1.0
+    def __init__(self, log2_box_dim, target_boxes_per_rank, my_rank=0, num_ranks=1, cheby=False, build_operator=True,
+                 bc=api.BC_DIRICHLET, library=None, a=0.0, b=1.0, vectors=None):
+        self.L = library or ref(cheby)
+        self.a, self.b = float(a), float(b)
         self.box_dim, self.boxes_in_i = api.problem_size(log2_box_dim, target_boxes_per_rank, num_ranks)
         self._level_buf = level_type()
         self.level_h = C.pointer(self._level_buf)
@@ -145,12 +146,16 @@ class RefHierarchy:
         self.mg = C.pointer(self._mg_buf)
         self.built = False
         with quiet():
-            self.L.create_level(self.level_h, self.boxes_in_i, self.box_dim, 2, api.VECTORS_RESERVED, api.BC_DIRICHLET, my_rank, num_ranks)
+            self.L.create_level(self.level_h, self.boxes_in_i, self.box_dim, 2, api.VECTORS_RESERVED if vectors is None else vectors, bc, my_rank, num_ranks)
             self.h = 1.0 / (float(self.boxes_in_i) * float(self.box_dim))
             if build_operator:
                 self.L.initialize_problem(self.level_h, self.h, self.a, self.b)
                 self.L.rebuild_operator(self.level_h, None, self.a, self.b)
-                self.L.MGBuild(self.mg, self.level_h, self.a, self.b, 1)
+                if bc == api.BC_PERIODIC:              # hpgmg-fv.c:296-302
+                    average = self.L.mean(self.level_h, api.VECTOR_F)
+                    if average != 0.0:
+                        self.L.shift_vector(self.level_h, api.VECTOR_F, api.VECTOR_F, -average)
+                self.L.MGBuild(self.mg, self.level_h, self.a, self.b, 2 if bc == api.BC_PERIODIC else 1)
                 self.built = True
 
     def build_lists_only(self):

@@ -127,6 +127,63 @@ def test_fmg_solve_host_buffers(gpu_lib):
         gpu_lib.hpgmg_b200_use_graphs(1)
 
 
+@pytest.mark.gpu
+def test_pipelined_host_solves_equal_the_serial_call(gpu_lib):
+    """hpgmg_fmg_solve_host_submit / _wait: a stream of solves with two in flight (upload of the next and download of the
+    previous one overlap the running solve).  Alternating right-hand sides f and 2f: every ticket must return exactly
+    what the serial call returns for ITS input, in pinned and in pageable host memory."""
+    with api.Hierarchy(5, 8) as H:
+        lvl = H.level(0)
+        Lc = lvl.contents
+        n, nb = Lc.box_dim, Lc.num_my_boxes
+        f1 = np.concatenate([np.ascontiguousarray(api.interior(lvl, api.download(lvl, b, api.VECTOR_F))).reshape(-1) for b in range(nb)])
+        fs = [f1, 2.0 * f1]
+        want = []
+        for f in fs:
+            u = np.zeros_like(f)
+            r = gpu_lib.hpgmg_fmg_solve_host(H.mg, 0, api.VECTOR_U, api.VECTOR_F, 0.0, 1.0, 1e-10, f.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p))
+            want.append((r, u))
+        assert want[0][0] == ob.goldens()["solves"]["5 8 gsrb"]["norms"][0]
+        assert want[1][0] != want[0][0]
+        nbytes = f1.nbytes
+        pinned = [gpu_lib.hpgmg_b200_host_alloc_pinned(nbytes) for _ in range(4)]
+        try:
+            for use_pinned in (True, False):
+                us = [np.full_like(f1, np.nan) for _ in range(2)]
+                if use_pinned:
+                    for q in range(2):
+                        C.memmove(pinned[q], fs[q].ctypes.data, nbytes)
+                    fin = [pinned[0], pinned[1]]
+                    uout = [pinned[2], pinned[3]]
+                else:
+                    fin = [f.ctypes.data_as(C.c_void_p) for f in fs]
+                    uout = [u.ctypes.data_as(C.c_void_p) for u in us]
+                tickets = []
+                got = []
+
+                def finish():
+                    q, t = tickets.pop(0)
+                    r = gpu_lib.hpgmg_fmg_solve_host_wait(H.mg, t)
+                    if use_pinned:
+                        C.memmove(us[q].ctypes.data, pinned[2 + q], nbytes)
+                    got.append((q, r, us[q].copy()))
+                    us[q][:] = np.nan
+                for step in range(7):
+                    q = step % 2
+                    if len(tickets) == 2:
+                        finish()
+                    tickets.append((q, gpu_lib.hpgmg_fmg_solve_host_submit(H.mg, 0, api.VECTOR_U, api.VECTOR_F, 0.0, 1.0, 1e-10, fin[q], uout[q])))
+                while tickets:
+                    finish()
+                assert len(got) == 7
+                for q, r, u in got:
+                    assert r == want[q][0]
+                    np.testing.assert_array_equal(u, want[q][1])
+        finally:
+            for p_ in pinned:
+                gpu_lib.hpgmg_b200_host_free_pinned(p_)
+
+
 # ------------------------------------------------------------------------------ operator by operator
 def mirror_random(H, R, rng, levels, ids):
     """Identical seeded data (ghost zones included) in our device level and the reference's host level."""

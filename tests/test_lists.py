@@ -36,15 +36,19 @@ def test_lists_equal_reference_goldens(layout_lib, key):
 
 
 @pytest.mark.skipif(not ob.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
-@pytest.mark.parametrize("log2,bpr,ranks", [(5, 8, 1), (4, 8, 2), (4, 8, 4), (4, 8, 8), (4, 2, 1)])
-def test_lists_equal_live_reference_entry_by_entry(layout_lib, log2, bpr, ranks):
+@pytest.mark.parametrize("log2,bpr,ranks,bc", [(5, 8, 1, 1), (4, 8, 2, 1), (4, 8, 4, 1), (4, 8, 8, 1), (4, 2, 1, 1),
+                                               (5, 8, 1, 0), (4, 1, 1, 0), (4, 8, 2, 0), (4, 27, 1, 0), (4, 8, 8, 0)])
+def test_lists_equal_live_reference_entry_by_entry(layout_lib, log2, bpr, ranks, bc):
     """Not just digests: every blockCopy_type of every list, field by field, against the reference
-    library called in this process."""
+    library called in this process.  bc 1: Dirichlet, 0: periodic (wrap-around neighbours, level.c:559-563, 757-761;
+    no BC blocks, level.c:371; the driver's minCoarseDim 2, hpgmg-fv.c:278)."""
     for r in range(ranks):
-        R = ob.RefHierarchy(log2, bpr, my_rank=r, num_ranks=ranks, build_operator=False)
-        R.build_lists_only()
-        H = api.Hierarchy(log2, bpr, my_rank=r, num_ranks=ranks, build_operator=False)
-        H.L.MGBuild(H.mg, H.level_h, 0.0, 1.0, 1)
+        R = ob.RefHierarchy(log2, bpr, my_rank=r, num_ranks=ranks, build_operator=False, bc=bc)
+        with ob.quiet():
+            R.L.MGBuild(R.mg, R.level_h, 0.0, 1.0, 1 if bc else 2)
+        R.built = True
+        H = api.Hierarchy(log2, bpr, my_rank=r, num_ranks=ranks, build_operator=False, bc=bc)
+        H.L.MGBuild(H.mg, H.level_h, 0.0, 1.0, 1 if bc else 2)
         H.built = True
         assert H.num_levels == R.num_levels
         for l in range(H.num_levels):
