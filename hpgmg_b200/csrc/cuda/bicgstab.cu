@@ -28,6 +28,9 @@ __global__ void __launch_bounds__(BOTTOM_THREADS) bicgstab_kernel(const BottomAr
  * recorded into a CUDA graph: the host-driven fallback synchronises on every dot / norm) */
 extern "C" int hpgmg_bicgstab_device_eligible(const level_type *level)
 {
+#ifdef VECTOR_ALPHA
+  return 0;                                        /* Helmholtz build: host-driven BiCGStab over the public operators (solvers.c) */
+#endif
   if (level->must_subtract_mean == 1) return 0;
   if (level->boundary_condition.type != BC_DIRICHLET) return 0;
   if (level->num_my_boxes != 1) return 0;

@@ -526,6 +526,9 @@ extern "C" int hpgmg_coarse_chain_eligible(mg_type *MG, int from)
     if (f) g_coarse_fast = atoi(f);
   }
   if (!g_coarse_enabled) return 0;
+#ifdef VECTOR_ALPHA
+  return 0;                                        /* Helmholtz build: the global-memory kernels carry the a*alpha*x term */
+#endif
   const int bottom = MG->num_levels - 1;
   if (from > bottom || bottom - from + 1 > COARSE_MAX_LEVELS) return 0;
   if (coarse_program_length(bottom - from + 1, 1) > COARSE_MAX_PHASES) return 0;

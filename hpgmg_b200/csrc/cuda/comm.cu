@@ -323,6 +323,35 @@ struct P2PWire {                                   /* what a rank tells the othe
   long long ll_off[P2P_MAX_NEIGHBOURS];            /* offset of the 2 x recv_size slot arrays in my arena */
 };
 
+#define P2P_CHUNK_CELLS 2048
+static void split_large_entries(std::vector<blockCopy_type> &list)
+{
+  static int chunk = -1;
+  if (chunk < 0) { const char *e = getenv("HPGMG_B200_P2P_CHUNK"); chunk = e ? atoi(e) : P2P_CHUNK_CELLS; }
+  if (chunk <= 0) return;
+  std::vector<blockCopy_type> out;
+  for (size_t e = 0; e < list.size(); e++) {
+    const blockCopy_type B = list[e];
+    const long cells = (long)B.dim.i * B.dim.j * B.dim.k;
+    if (cells <= chunk) { out.push_back(B); continue; }
+    int cj = chunk / B.dim.i;                         /* rows of a slab */
+    if (cj < 1) cj = 1;
+    if (cj > B.dim.j) cj = B.dim.j;
+    int ck = (cj == B.dim.j) ? chunk / (B.dim.i * B.dim.j) : 1;   /* whole planes only if a plane fits */
+    if (ck < 1) ck = 1;
+    for (int k0 = 0; k0 < B.dim.k; k0 += ck)
+      for (int j0 = 0; j0 < B.dim.j; j0 += cj) {
+        blockCopy_type S = B;
+        S.dim.j = (j0 + cj <= B.dim.j) ? cj : B.dim.j - j0;
+        S.dim.k = (k0 + ck <= B.dim.k) ? ck : B.dim.k - k0;
+        S.read.j += j0;   S.read.k += k0;
+        S.write.j += j0;  S.write.k += k0;
+        out.push_back(S);
+      }
+  }
+  list.swap(out);
+}
+
 extern "C" void hpgmg_comm_register_exchange(level_type *level, int shape)
 {
   if (!g_p2p_enabled || g_nranks <= 1 || hpgmg_rt_layout_only()) return;
@@ -375,6 +404,11 @@ extern "C" void hpgmg_comm_register_exchange(level_type *level, int shape)
     if (n < 0) { fprintf(stderr, "hpgmg_b200: unpack entry without a receive buffer\n"); exit(1); }
     unpack[e].subtype = n;
   }
+  /* One thread block works off one list entry.  A face of a 128^3 box is 32768 cells: 24 such blocks per fill would carry
+   * the whole NVLink traffic of a rank on 24 of its 148 SMs.  Cut large entries into slabs of <= P2P_CHUNK_CELLS along j
+   * (then k); an entry's read and write side index the same (i,j,k), so a slab is the entry with shifted origins. */
+  split_large_entries(pack);
+  split_large_entries(unpack);
   H.npack = (int)pack.size();  H.nunpack = (int)unpack.size();
   if (H.npack) { CUDA_CHECK(cudaMalloc(&H.pack, pack.size() * sizeof(blockCopy_type))); CUDA_CHECK(cudaMemcpy(H.pack, pack.data(), pack.size() * sizeof(blockCopy_type), cudaMemcpyHostToDevice)); }
   if (H.nunpack) { CUDA_CHECK(cudaMalloc(&H.unpack, unpack.size() * sizeof(blockCopy_type))); CUDA_CHECK(cudaMemcpy(H.unpack, unpack.data(), unpack.size() * sizeof(blockCopy_type), cudaMemcpyHostToDevice)); }

@@ -164,7 +164,7 @@ __device__ __forceinline__ void fill_block(const FillArgs &A, const int fb)
   }
 }
 
-__global__ void __launch_bounds__(256) fill_ghosts_kernel(const FillArgs A)
+__global__ void __launch_bounds__(256, 4) fill_ghosts_kernel(const FillArgs A)
 {
   PDL_WAIT();
   const DLevel &L = A.L;

@@ -15,6 +15,18 @@
 
 enum { OP_APPLY = 0, OP_RESIDUAL = 1, OP_GSRB = 2, OP_CHEBY = 3, OP_REBUILD = 4 };
 
+/* The Helmholtz build (-DUSE_HELMHOLTZ, as in the reference: operators.fv4.c:56-85): A x = a*alpha*x - b*h2inv*(...).  The
+ * reference subtracts (b*h2inv)*(...) from a*alpha*x; fv4_apply_op returns (-b*h2inv)*(...), the exact negation, and
+ * p - q == p + (-q) in IEEE arithmetic, so the sum below has the reference's bits.  In that build every operator goes
+ * through the two global-memory kernels of this file (no TMA / fused-box / single-block paths). */
+#ifdef VECTOR_ALPHA
+#define HELMHOLTZ_TERM(a, alpha, x) (a) * (alpha) * (x) +
+#define VECTOR_ALPHA_OR_0 VECTOR_ALPHA
+#else
+#define HELMHOLTZ_TERM(a, alpha, x)
+#define VECTOR_ALPHA_OR_0 0
+#endif
+
 struct StencilArgs {
   DLevel L;
   const int *low;          /* [nboxes][3] */
@@ -53,7 +65,7 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(const StencilArgs 
     double *__restrict__ out = L.vec(box, A.out_id) + ijk;
     const int color000 = (A.low[3 * box] ^ A.low[3 * box + 1] ^ A.low[3 * box + 2] ^ A.sweep) & 1;
     if (((i ^ j ^ k ^ color000) & 1) == 0) {
-      const double Ax = fv4_apply_op(x, bi, bj, bk, jS, kS, A.b, A.h2inv);
+      const double Ax = HELMHOLTZ_TERM(A.a, L.vec(box, VECTOR_ALPHA_OR_0)[ijk], x[0]) fv4_apply_op(x, bi, bj, bk, jS, kS, A.b, A.h2inv);
       const double dinv = L.vec(box, VECTOR_DINV)[ijk];
       const double rhs = L.vec(box, A.rhs_id)[ijk];
       out[0] = x[0] + dinv * (rhs - Ax);
@@ -62,7 +74,7 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(const StencilArgs 
     }
     return;
   }
-  const double Ax = fv4_apply_op(x, bi, bj, bk, jS, kS, A.b, A.h2inv);
+  const double Ax = HELMHOLTZ_TERM(A.a, L.vec(box, VECTOR_ALPHA_OR_0)[ijk], x[0]) fv4_apply_op(x, bi, bj, bk, jS, kS, A.b, A.h2inv);
   if (OP == OP_APPLY) {
     L.vec(box, A.out_id)[ijk] = Ax;
   } else if (OP == OP_RESIDUAL) {
@@ -205,14 +217,14 @@ __global__ void __launch_bounds__(256) stencil_pair_kernel(const StencilArgs A)
     const int a = (j ^ k ^ color000) & 1;                     /* the active cell of the pair */
     const double2 rhs2 = *reinterpret_cast<const double2 *>(L.vec(box, A.rhs_id) + ijk);
     const double2 dinv2 = *reinterpret_cast<const double2 *>(L.vec(box, VECTOR_DINV) + ijk);
-    const double Ax = fv4_apply_op(x + a, bi + a, bj + a, bk + a, jS, kS, A.b, A.h2inv);
+    const double Ax = HELMHOLTZ_TERM(A.a, L.vec(box, VECTOR_ALPHA_OR_0)[ijk + a], x[a]) fv4_apply_op(x + a, bi + a, bj + a, bk + a, jS, kS, A.b, A.h2inv);
     const double xnew = x[a] + (a ? dinv2.y : dinv2.x) * ((a ? rhs2.y : rhs2.x) - Ax);
     const double xo = x[1 - a];
     *out = a ? make_double2(xo, xnew) : make_double2(xnew, xo);
     return;
   }
-  const double Ax0 = fv4_apply_op(x, bi, bj, bk, jS, kS, A.b, A.h2inv);
-  const double Ax1 = fv4_apply_op(x + 1, bi + 1, bj + 1, bk + 1, jS, kS, A.b, A.h2inv);
+  const double Ax0 = HELMHOLTZ_TERM(A.a, L.vec(box, VECTOR_ALPHA_OR_0)[ijk], x[0]) fv4_apply_op(x, bi, bj, bk, jS, kS, A.b, A.h2inv);
+  const double Ax1 = HELMHOLTZ_TERM(A.a, L.vec(box, VECTOR_ALPHA_OR_0)[ijk + 1], x[1]) fv4_apply_op(x + 1, bi + 1, bj + 1, bk + 1, jS, kS, A.b, A.h2inv);
   if (OP == OP_APPLY) { *out = make_double2(Ax0, Ax1); return; }
   const double2 rhs2 = *reinterpret_cast<const double2 *>(L.vec(box, A.rhs_id) + ijk);
   if (OP == OP_RESIDUAL) { *out = make_double2(rhs2.x - Ax0, rhs2.y - Ax1); return; }
@@ -238,8 +250,13 @@ static void launch_stencil(level_type *level, StencilArgs &A)
   const int n = L.dim;
   stencil_env();
   if (OP != OP_REBUILD && hpgmg_ablate(n < 64 ? 8 : (OP == OP_RESIDUAL ? 32 : 64))) return;
+#ifdef VECTOR_ALPHA
+  A.diag = 0;                                                                     /* the diagonal carries a*alpha */
+#endif
   if (OP != OP_REBUILD && !g_force_generic) {
+#ifndef VECTOR_ALPHA
     if (n % 32 == 0 && g_tma) { launch_tma<OP, 32, 8, 1, 4>(A); return; }       /* boxes of 32^3 .. 256^3 */
+#endif
     if ((n & 1) == 0 && n >= 4 && g_pair_kernel) {
       const int hn = n / 2;
       dim3 block(hn >= 16 ? 16 : hn, n >= 8 ? 8 : n, hn >= 16 ? 2 : (n >= 8 ? 256 / (hn * 8) : 256 / (hn * n)));
@@ -286,6 +303,9 @@ static int try_launch_box(level_type *level, const StencilArgs &S, const int wri
   hpgmg_device_level *D = HPGMG_DEV(level);
   const TileTable &T = D->tile_fill;
   const int n = level->box_dim;
+#ifdef VECTOR_ALPHA
+  return 0;
+#endif
   if (g_force_generic || n > g_box_fused_max || T.ntiles == 0 || level->num_my_boxes == 0) return 0;
   if (D->fill_nvec != level->numVectors || level->box_ghosts != 2 || level->box_jStride != ((n + 4 + 3) / 4) * 4) return 0;
   if (hpgmg_ablate(n < 64 ? 8 : 64)) return 1;
@@ -461,7 +481,11 @@ extern "C" void rebuild_operator_blackbox(level_type *level, double a, double b,
     fprintf(stdout, "  calculating D^{-1} exactly for level h=%e using %3d colors...  ", level->h, colors_in_each_dim * colors_in_each_dim * colors_in_each_dim);
     fflush(stdout);
   }
+#ifdef VECTOR_L1INV
+  const int x_id = VECTOR_TEMP, Aii_id = VECTOR_DINV, sum_id = VECTOR_L1INV;      /* rebuild.c:77-81 */
+#else
   const int x_id = VECTOR_TEMP, Aii_id = VECTOR_DINV, sum_id = VECTOR_E;
+#endif
   zero_vector(level, Aii_id);
   zero_vector(level, sum_id);
   for (int kc = 0; kc < colors_in_each_dim; kc++)
@@ -495,11 +519,17 @@ extern "C" void rebuild_operator_blackbox(level_type *level, double a, double b,
 extern "C" void rebuild_operator(level_type *level, level_type *fromLevel, double a, double b)
 {
   if (fromLevel != NULL) {
+#ifdef VECTOR_ALPHA
+    restriction(level, VECTOR_ALPHA, fromLevel, VECTOR_ALPHA, RESTRICT_CELL);
+#endif
     restriction(level, VECTOR_BETA_I, fromLevel, VECTOR_BETA_I, RESTRICT_FACE_I);
     restriction(level, VECTOR_BETA_J, fromLevel, VECTOR_BETA_J, RESTRICT_FACE_J);
     restriction(level, VECTOR_BETA_K, fromLevel, VECTOR_BETA_K, RESTRICT_FACE_K);
   }
   extrapolate_betas(level);
+#ifdef VECTOR_ALPHA
+  exchange_boundary(level, VECTOR_ALPHA, STENCIL_SHAPE_BOX);
+#endif
   exchange_boundary(level, VECTOR_BETA_I, STENCIL_SHAPE_BOX);
   exchange_boundary(level, VECTOR_BETA_J, STENCIL_SHAPE_BOX);
   exchange_boundary(level, VECTOR_BETA_K, STENCIL_SHAPE_BOX);

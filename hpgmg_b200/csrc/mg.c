@@ -449,9 +449,14 @@ void MGBuild(mg_type *MG, level_type *fine, double a, double b, int minCoarseGri
 
   for (int l = 0; l < MG->num_levels; l++) {
     level_type *L = MG->levels[l];
-    /* Poisson-like with periodic BCs: the solution is only defined up to a constant.  There is
-     * no VECTOR_ALPHA in this build, so "alpha is zero" always holds (mg.c:1009-1018). */
+    /* Poisson-like with periodic BCs: the solution is only defined up to a constant (mg.c:1009-1018).  Without
+     * VECTOR_ALPHA "alpha is zero" always holds. */
+#ifdef VECTOR_ALPHA
+    const int alpha_is_zero = (dot(L, VECTOR_ALPHA, VECTOR_ALPHA) == 0.0);
+    L->must_subtract_mean = (L->boundary_condition.type == BC_PERIODIC && (a == 0 || alpha_is_zero)) ? 1 : 0;
+#else
     L->must_subtract_mean = (L->boundary_condition.type == BC_PERIODIC) ? 1 : 0;
+#endif
   }
   hpgmg_rt_sync();
   MG->timers.MGBuild += hpgmg_rt_wtime() - t0;

@@ -79,6 +79,13 @@ void initialize_problem(level_type *L, double hLevel, double a, double b)
       F[ijk]  = evaluateF(x, y, z, hLevel, 1, 1, 1);
     }
     for (int v = 0; v < 4; v++) hpgmg_upload_box_vector(L, box, ids[v], stage + v * vol);
+#ifdef VECTOR_ALPHA
+    /* A = 1.0 on the same index range (problem.fv.c:118,129-131); stage[0] is free again */
+    hpgmg_download_box_vector(L, box, VECTOR_ALPHA, stage);
+    for (int k = 0; k <= n; k++) for (int j = 0; j <= n; j++) for (int i = 0; i <= n; i++)
+      stage[(size_t)(i + g) + (size_t)(j + g) * jS + (size_t)(k + g) * kS] = 1.0;
+    hpgmg_upload_box_vector(L, box, VECTOR_ALPHA, stage);
+#endif
   }
   hpgmg_rt_sync();
   free(stage);

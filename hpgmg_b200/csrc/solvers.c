@@ -77,8 +77,14 @@ static void bicgstab_host_driven(level_type *L, int x_id, int R_id, double a, do
 void IterativeSolver(level_type *L, int u_id, int f_id, double a, double b, double desired_reduction_in_norm)
 {
   if (!L->active) return;
-  if (L->must_subtract_mean == -1)
-    L->must_subtract_mean = (L->boundary_condition.type == BC_PERIODIC) ? 1 : 0;   /* solvers.c:30-38 */
+  if (L->must_subtract_mean == -1) {                                               /* solvers.c:30-38 */
+#ifdef VECTOR_ALPHA
+    const int alpha_is_zero = (dot(L, VECTOR_ALPHA, VECTOR_ALPHA) == 0.0);
+    L->must_subtract_mean = (L->boundary_condition.type == BC_PERIODIC && (a == 0 || alpha_is_zero)) ? 1 : 0;
+#else
+    L->must_subtract_mean = (L->boundary_condition.type == BC_PERIODIC) ? 1 : 0;
+#endif
+  }
   if (L->numVectors < VECTORS_RESERVED + IterativeSolver_NumVectors())
     create_vectors(L, VECTORS_RESERVED + IterativeSolver_NumVectors());
   if (hpgmg_bicgstab_device(L, u_id, f_id, a, b, desired_reduction_in_norm)) return;
