@@ -91,6 +91,26 @@ struct SlotLoader {
   }
 };
 
+/* The same load as a PURE function of (address, token): not volatile, so the two stencil evaluations of a thread that owns
+ * two cells share the operands they have in common (the compiler merges loads with identical operands: 85 instead of 110
+ * per cell pair).  The token is made by a volatile asm at the top of a march step, after the step's planes have landed, so
+ * a load can neither move above that point nor be merged with a load of another step. */
+__device__ __forceinline__ double lds_f64_pure(const unsigned a, const unsigned tok)
+{
+  double v;
+  asm("ld.shared.f64 %0, [%1]; // step %2" : "=d"(v) : "r"(a), "r"(tok));
+  return v;
+}
+template <int W, int DK0, int NPLANES>
+struct PureSlotLoader {
+  unsigned a[NPLANES];
+  unsigned tok;
+  __device__ __forceinline__ double operator()(const int di, const int dj, const int dk) const
+  {
+    return lds_f64_pure(a[dk - DK0] + (unsigned)((dj * W + di) * 8), tok);
+  }
+};
+
 /* PF: how many steps ahead the planes are requested.  MINB: resident blocks per SM the register budget is
  * sized for.  REV: march k downwards -- alternating the direction from sweep to sweep lets a sweep start
  * on the planes the previous sweep touched last, which are still in the 126 MB L2. */
@@ -116,13 +136,18 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
   const int n = L.dim, jS = L.jStride, kS = L.kStride;
   const int tiles_i = n / TI, tiles = tiles_i * (n / TJ);
 
-  /* lane -> (row, pair): even lanes row 2rp, odd lanes row 2rp+1; 16 consecutive pairs per warp */
+  /* GSRB: lane -> (row, i-pair): even lanes row 2rp, odd lanes row 2rp+1; 16 consecutive pairs per warp.
+   * The uncoloured operators (JP): a thread owns the J-pair (i, j), (i, j+1) -- lanes are consecutive cells of a row, so every
+   * 64-bit shared load of a warp is two conflict-free wavefronts, and the two cells share 25 of their 110 operands. */
+  constexpr bool JP = (OP != OP_GSRB);
+  static_assert(!JP || TI == 32, "the j-pair mapping puts one row of a tile on the lanes of a warp");
   constexpr int WPR = (TI / 2) / 16;                                /* warps per row pair */
   const int warp = tid >> 5, lane = tid & 31;
-  const int r = 2 * (warp / WPR) + (lane & 1);
+  const int r = JP ? 2 * warp : 2 * (warp / WPR) + (lane & 1);
   const int p = 16 * (warp % WPR) + (lane >> 1);
-  const unsigned lane_x = (unsigned)(((r + 2) * C::W + 2 + 2 * p) * 8);     /* even cell of the pair, x tile  */
-  const unsigned lane_b = (unsigned)(((r + 1) * C::W + 2 + 2 * p) * 8);     /* the same in the beta tiles     */
+  const int ci_lane = JP ? lane : 2 * p;                            /* first (only) cell of the thread within the tile row */
+  const unsigned lane_x = (unsigned)(((r + 2) * C::W + 2 + ci_lane) * 8);   /* the thread's first cell, x tile  */
+  const unsigned lane_b = (unsigned)(((r + 1) * C::W + 2 + ci_lane) * 8);   /* the same in the beta tiles       */
 
   /* my share of the linearised (box, tile, k) space */
   const long long lo = total_planes * (long long)blockIdx.x / (long long)gridDim.x;
@@ -170,7 +195,7 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
     }
 
     const int j = j0 + r;
-    const int cell = (i0 + 2 * p) + j * jS;                        /* pair (2p, 2p+1) of row j, plane 0 */
+    const int cell = (i0 + ci_lane) + j * jS;                      /* GSRB: pair (2p, 2p+1) of row j; JP: cells (lane, j), (lane, j+1); plane 0 */
     const double *g_rhs = (OP == OP_APPLY) ? nullptr : L.vec(box, A.rhs_id) + cell;
     const double *g_dinv = (OP == OP_GSRB || OP == OP_CHEBY) ? L.vec(box, VECTOR_DINV) + cell : nullptr;
     const double *g_xm1 = (OP == OP_CHEBY) ? L.vec(box, A.xm1_id) + cell : nullptr;
@@ -195,9 +220,10 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
 
     /* point-wise operands (rhs, Dinv, x_{n-1}) are read one plane ahead into registers */
     double2 rhs_n = make_double2(0.0, 0.0), dinv_n = make_double2(0.0, 0.0), xm_n = make_double2(0.0, 0.0);
-    if (OP != OP_APPLY) rhs_n = *reinterpret_cast<const double2 *>(g_rhs + kf * kS);
-    if ((OP == OP_GSRB || OP == OP_CHEBY) && PLANE_NEEDS_DINV(kf)) dinv_n = *reinterpret_cast<const double2 *>(g_dinv + kf * kS);
-    if (OP == OP_CHEBY) xm_n = *reinterpret_cast<const double2 *>(g_xm1 + kf * kS);
+#define LOAD_PAIR(ptr, kk) (JP ? make_double2((ptr)[(kk) * kS], (ptr)[(kk) * kS + jS]) : *reinterpret_cast<const double2 *>((ptr) + (kk) * kS))
+    if (OP != OP_APPLY) rhs_n = LOAD_PAIR(g_rhs, kf);
+    if ((OP == OP_GSRB || OP == OP_CHEBY) && PLANE_NEEDS_DINV(kf)) dinv_n = LOAD_PAIR(g_dinv, kf);
+    if (OP == OP_CHEBY) xm_n = LOAD_PAIR(g_xm1, kf);
 
     mbar_wait(bar0, phasebits & 1u);                               /* step 0's planes */
     phasebits ^= 1u;
@@ -222,9 +248,9 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
       }
       const double2 rhs2 = rhs_n, dinv2 = dinv_n, xm2 = xm_n;
       if (more) {
-        if (OP != OP_APPLY) rhs_n = *reinterpret_cast<const double2 *>(g_rhs + (k + dir) * kS);
-        if ((OP == OP_GSRB || OP == OP_CHEBY) && PLANE_NEEDS_DINV(k + dir)) dinv_n = *reinterpret_cast<const double2 *>(g_dinv + (k + dir) * kS);
-        if (OP == OP_CHEBY) xm_n = *reinterpret_cast<const double2 *>(g_xm1 + (k + dir) * kS);
+        if (OP != OP_APPLY) rhs_n = LOAD_PAIR(g_rhs, k + dir);
+        if ((OP == OP_GSRB || OP == OP_CHEBY) && PLANE_NEEDS_DINV(k + dir)) dinv_n = LOAD_PAIR(g_dinv, k + dir);
+        if (OP == OP_CHEBY) xm_n = LOAD_PAIR(g_xm1, k + dir);
       }
 
       /* ---- slot addresses of this step's planes, indexed by plane offset (ring position r holds plane
@@ -258,30 +284,36 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
         out2 = s ? make_double2(xo, xnew) : make_double2(xnew, xo);
         s ^= 1;
       } else {
+        unsigned tok;
+        asm volatile("mov.u32 %0, %1;" : "=r"(tok) : "r"(t) : "memory");     /* this step's planes are in place from here on */
         double res[2];
 #pragma unroll
-        for (int t = 0; t < 2; t++) {
-          const int c = s ^ t;                                       /* cell of the pair evaluated in round t */
-          const unsigned so = (unsigned)(8 * c);
+        for (int c = 0; c < 2; c++) {                                  /* cell (lane, j + c) */
+          const unsigned so = (unsigned)(c * C::W * 8);
+          PureSlotLoader<C::W, -2, 5> PX;
+          PureSlotLoader<C::W, -1, 3> PBI, PBJ;
+          PureSlotLoader<C::W, 0, 2> PBK;
+          PX.tok = PBI.tok = PBJ.tok = PBK.tok = tok;
 #pragma unroll
-          for (int d = 0; d < 5; d++) X.a[d] = ax[d] + so;
+          for (int d = 0; d < 5; d++) PX.a[d] = ax[d] + so;
 #pragma unroll
-          for (int d = 0; d < 3; d++) { BI.a[d] = abi[d] + so; BJ.a[d] = abj[d] + so; }
+          for (int d = 0; d < 3; d++) { PBI.a[d] = abi[d] + so; PBJ.a[d] = abj[d] + so; }
 #pragma unroll
-          for (int d = 0; d < 2; d++) BK.a[d] = abk[d] + so;
-          const double Ax = fv4_apply_op_at(X, BI, BJ, BK, A.b, A.h2inv);
+          for (int d = 0; d < 2; d++) PBK.a[d] = abk[d] + so;
+          const double Ax = fv4_apply_op_at(PX, PBI, PBJ, PBK, A.b, A.h2inv);
           double v;
           if (OP == OP_APPLY) v = Ax;
           else if (OP == OP_RESIDUAL) { v = (c ? rhs2.y : rhs2.x) - Ax; const double f = fabs(v); if (f > vmax) vmax = f; }
           else {                                                     /* OP_CHEBY, chebyshev.c:90 */
-            const double xn = X(0, 0, 0);
+            const double xn = PX(0, 0, 0);
             v = xn + A.c1 * (xn - (c ? xm2.y : xm2.x)) + A.c2 * (c ? dinv2.y : dinv2.x) * ((c ? rhs2.y : rhs2.x) - Ax);
           }
-          res[t] = v;
+          res[c] = v;
         }
-        out2 = s ? make_double2(res[1], res[0]) : make_double2(res[0], res[1]);
+        out2 = make_double2(res[0], res[1]);
       }
-      *reinterpret_cast<double2 *>(g_out + k * kS) = out2;
+      if (JP) { g_out[k * kS] = out2.x; g_out[k * kS + jS] = out2.y; }
+      else *reinterpret_cast<double2 *>(g_out + k * kS) = out2;
 
       sx = sx + 1 == C::XP ? 0 : sx + 1;
       sb = sb + 1 == C::BP ? 0 : sb + 1;
@@ -294,6 +326,7 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
       __syncthreads();                                               /* everyone is done with the oldest slots */
     }
 #undef PLANE_NEEDS_DINV
+#undef LOAD_PAIR
   }
   if (OP == OP_RESIDUAL && A.norm_slot != nullptr) {                /* norm(): misc.c:287-329, max of |res| */
 #pragma unroll
