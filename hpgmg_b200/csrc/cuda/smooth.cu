@@ -111,6 +111,7 @@ static void stencil_env(void)
   if ((e = getenv("HPGMG_B200_ZIGZAG")) != NULL) g_zigzag = atoi(e);           /* 0: every sweep marches k upwards */
   if ((e = getenv("HPGMG_B200_DIAG")) != NULL) g_diag = atoi(e);               /* 0: Dinv always read from memory */
   if ((e = getenv("HPGMG_B200_PAIR_KERNEL")) != NULL) g_pair_kernel = atoi(e); /* 0: small boxes through the generic kernel */
+  if ((e = getenv("HPGMG_B200_TMA_MINPLANES")) != NULL && atoi(e) > 0) g_tma_minplanes = atoi(e);   /* shortest k-chunk a block may get */
   if ((e = getenv("HPGMG_B200_BOX_FUSED_MAX")) != NULL) g_box_fused_max = atoi(e);   /* largest box the fill-fused kernels take (0: none, 32: also the TMA kernel's smallest size) */
 }
 
