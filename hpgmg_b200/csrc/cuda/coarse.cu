@@ -29,12 +29,10 @@
  * (tests/test_gpu_parity.py::test_coarse_kernel_equals_multilaunch_path).
  */
 #include <math.h>
-#include <cooperative_groups.h>
 #include "common.cuh"
 #include "stencil.cuh"
 #include "bc.cuh"
 #include "bicgstab.cuh"
-namespace cg = cooperative_groups;
 
 #define COARSE_MAX_LEVELS 8
 #define COARSE_THREADS    512
@@ -59,10 +57,6 @@ struct CoarseLevel {
   int smem_offset;                                /* >=0: resident, doubles from the start of the pool */
   int nslots;
   int fast;                                       /* 8, 4, 2: resident single box of that size, specialised bodies; 0: generic */
-  int clustered;                                  /* the level is 2^3 boxes of 8^3, ONE PER THREAD BLOCK of an 8-block cluster: TEMP, e, R of the block's
-                                                     box are resident (slots 0..2), the operator data is read from global memory, ghost cells across a
-                                                     box seam come out of the neighbouring block's shared memory */
-  int gnvec;                                      /* vectors per box of the global slab */
   int s_dinv, s_bi, s_bj, s_bk;                   /* slots of the operator data */
   unsigned char slot_id[COARSE_MAX_SLOTS];        /* slot -> vector id */
   unsigned char slot_io[COARSE_MAX_SLOTS];        /* bit 0: load at entry, bit 1: store at exit */
@@ -213,43 +207,10 @@ __device__ __forceinline__ void c_pro5(const double cmm, const double cm, const 
 
 /* interpolation_v2.c:112-172 (W=3) / interpolation_v4.c:149-238 (W=5) over the coarse level's local list: one thread per
  * coarse cell; i-pass and j-pass plane by plane, then the k-pass (the order of interpolation_kernel, transfer.cu) */
-/* one coarse cell -> its 8 fine cells: r points at the coarse cell (strides rj, rk), w at the fine cell (2i,2j,2k) (strides wj, wk) */
-template <int W>
-__device__ __forceinline__ void c_interp_cell(const double *r, const int rj, const int rk, double *w, const int wj, const int wk, const double prescale)
-{
-  constexpr int R = W / 2;
-  double fj[2][2][W];
-#pragma unroll
-  for (int K = 0; K < W; K++) {
-    double fi[2][W];
-#pragma unroll
-    for (int J = 0; J < W; J++) {
-      const double *p = r + (J - R) * rj + (K - R) * rk;
-      if constexpr (W == 3) c_pro3(p[-1], p[0], p[1], fi[0][J], fi[1][J]);
-      else                  c_pro5(p[-2], p[-1], p[0], p[1], p[2], fi[0][J], fi[1][J]);
-    }
-#pragma unroll
-    for (int I = 0; I < 2; I++) {
-      if constexpr (W == 3) c_pro3(fi[I][0], fi[I][1], fi[I][2], fj[I][0][K], fj[I][1][K]);
-      else                  c_pro5(fi[I][0], fi[I][1], fi[I][2], fi[I][3], fi[I][W - 1], fj[I][0][K], fj[I][1][K]);
-    }
-  }
-#pragma unroll
-  for (int J = 0; J < 2; J++)
-#pragma unroll
-  for (int I = 0; I < 2; I++) {
-    double lo, hi;
-    if constexpr (W == 3) c_pro3(fj[I][J][0], fj[I][J][1], fj[I][J][2], lo, hi);
-    else                  c_pro5(fj[I][J][0], fj[I][J][1], fj[I][J][2], fj[I][J][3], fj[I][J][W - 1], lo, hi);
-    double *w0 = w + I + J * wj;
-    w0[0] = prescale * w0[0] + lo;
-    w0[wk] = prescale * w0[wk] + hi;
-  }
-}
-
 template <int W>
 __device__ static void c_interpolate(const DLevel &Lf, const int slot_f, const double prescale, const DLevel &Lc, const int slot_c, const blockCopy_type *blocks, const int n, const int entry_cells)
 {
+  constexpr int R = W / 2;
   const int rj = Lc.jStride, rk = Lc.kStride, wj = Lf.jStride, wk = Lf.kStride;
   for (int wi = threadIdx.x; wi < n * entry_cells; wi += blockDim.x) {
     const int e = wi / entry_cells, c = wi - e * entry_cells;
@@ -258,8 +219,34 @@ __device__ static void c_interpolate(const DLevel &Lf, const int slot_f, const d
     if (c >= di * dj * B.dim.k) continue;
     const int ii = c % di, jj = (c / di) % dj, kk = c / (di * dj);
     const double *r = Lc.vec(B.read.box, slot_c) + (ii + B.read.i) + (jj + B.read.j) * rj + (kk + B.read.k) * rk;
+    double fj[2][2][W];
+#pragma unroll
+    for (int K = 0; K < W; K++) {
+      double fi[2][W];
+#pragma unroll
+      for (int J = 0; J < W; J++) {
+        const double *p = r + (J - R) * rj + (K - R) * rk;
+        if constexpr (W == 3) c_pro3(p[-1], p[0], p[1], fi[0][J], fi[1][J]);
+        else                  c_pro5(p[-2], p[-1], p[0], p[1], p[2], fi[0][J], fi[1][J]);
+      }
+#pragma unroll
+      for (int I = 0; I < 2; I++) {
+        if constexpr (W == 3) c_pro3(fi[I][0], fi[I][1], fi[I][2], fj[I][0][K], fj[I][1][K]);
+        else                  c_pro5(fi[I][0], fi[I][1], fi[I][2], fi[I][3], fi[I][W - 1], fj[I][0][K], fj[I][1][K]);
+      }
+    }
     double *w = Lf.vec(B.write.box, slot_f) + (2 * ii + B.write.i) + (2 * jj + B.write.j) * wj + (2 * kk + B.write.k) * wk;
-    c_interp_cell<W>(r, rj, rk, w, wj, wk, prescale);
+#pragma unroll
+    for (int J = 0; J < 2; J++)
+#pragma unroll
+    for (int I = 0; I < 2; I++) {
+      double lo, hi;
+      if constexpr (W == 3) c_pro3(fj[I][J][0], fj[I][J][1], fj[I][J][2], lo, hi);
+      else                  c_pro5(fj[I][J][0], fj[I][J][1], fj[I][J][2], fj[I][J][3], fj[I][J][W - 1], lo, hi);
+      double *w0 = w + I + J * wj;
+      w0[0] = prescale * w0[0] + lo;
+      w0[wk] = prescale * w0[wk] + hi;
+    }
   }
 }
 
@@ -309,11 +296,14 @@ __device__ static void c_fill_fast(double *v, const bool box_shape, const bool f
 /* one sweep / residual of ONE box of N^3 cells whose low corner is the domain's; `base` points at cell (0,0,0) of slot 0,
  * strides Geo<N>.  GSRB: one thread per i-pair = per updated cell; Chebyshev / residual: one thread per cell. */
 template <int N>
-__device__ static void c_stencil_fast_ptr(const double *x, double *out, const double *rhs, const double *dinv, const double *bi, const double *bj, const double *bk,
-                                          const double h2inv, const double c1, const double c2, const int mode, const int s, const double b)
+__device__ static void c_stencil_fast(const CoarseLevel &V, double *base, const int mode, const int src, const int dst, const int rhs_slot, const int s, const double b)
 {
   typedef Geo<N> G;
   constexpr int LG = N == 8 ? 3 : (N == 4 ? 2 : 1);
+  const double *x = base + src * G::VOL, *bi = base + V.s_bi * G::VOL, *bj = base + V.s_bj * G::VOL, *bk = base + V.s_bk * G::VOL;
+  const double *rhs = base + rhs_slot * G::VOL, *dinv = base + V.s_dinv * G::VOL;
+  double *out = base + dst * G::VOL;
+  const double h2inv = V.h2inv;
   const int work = mode == 0 ? N * N * N / 2 : N * N * N;
   for (int q = threadIdx.x; q < work; q += blockDim.x) {
     int i, j, k;
@@ -326,7 +316,7 @@ __device__ static void c_stencil_fast_ptr(const double *x, double *out, const do
       } else {
         p = q & (N / 2 - 1);  j = (q >> (LG - 1)) & (N - 1);  k = q >> (2 * LG - 1);
       }
-      i = 2 * p + ((j ^ k ^ s) & 1);                                /* the pair's active cell (gsrb.c:55,100); box low is even in every direction */
+      i = 2 * p + ((j ^ k ^ s) & 1);                                /* the pair's active cell (gsrb.c:55,100); box low = 0,0,0 */
     } else {
       i = q & (N - 1);  j = (q >> LG) & (N - 1);  k = q >> (2 * LG);
     }
@@ -341,122 +331,8 @@ __device__ static void c_stencil_fast_ptr(const double *x, double *out, const do
       out[ijk] = rhs[ijk] - Ax;
     } else {
       const double xn = x[ijk];
-      out[ijk] = xn + c1 * (xn - out[ijk]) + c2 * dinv[ijk] * (rhs[ijk] - Ax);     /* x_{n-1} aliases x_{n+1} (chebyshev.c:75-80) */
+      out[ijk] = xn + V.c1[s] * (xn - out[ijk]) + V.c2[s] * dinv[ijk] * (rhs[ijk] - Ax);     /* x_{n-1} aliases x_{n+1} (chebyshev.c:75-80) */
     }
-  }
-}
-/* one sweep / residual of ONE resident box of N^3 cells whose low corner is even; `base` points at cell (0,0,0) of slot 0,
- * strides Geo<N>.  GSRB: one thread per i-pair = per updated cell; Chebyshev / residual: one thread per cell. */
-template <int N>
-__device__ static void c_stencil_fast(const CoarseLevel &V, double *base, const int mode, const int src, const int dst, const int rhs_slot, const int s, const double b)
-{
-  typedef Geo<N> G;
-  c_stencil_fast_ptr<N>(base + src * G::VOL, base + dst * G::VOL, base + rhs_slot * G::VOL, base + V.s_dinv * G::VOL, base + V.s_bi * G::VOL, base + V.s_bj * G::VOL,
-                        base + V.s_bk * G::VOL, V.h2inv, V.c1[s], V.c2[s], mode, s, b);
-}
-
-/* ---- the clustered level: 2^3 boxes of N^3, one per thread block of the cluster ---------------------------------------- */
-/* Ghost fill of THIS block's box.  `v` points at cell (0,0,0) of the vector in this block's shared memory; every block keeps the
- * vector at the same shared-memory address, so the same cell of a neighbouring box is map_shared_rank(pointer, its rank).
- * bx[a] in {0,1}: the box's position; along axis a the side facing the other box is a SEAM (ghost cells = the neighbour's interior
- * cells, exchange_boundary), the other side the DOMAIN boundary (boundary condition).  A ghost region r in {-1,0,1}^3 whose
- * outside axes are all seams is copied; otherwise it is a set of BC columns along the domain axes, read -- where the region also
- * crosses a seam -- from the neighbour across that seam (the image device_level.cu resolves into FillBC::src).  Same column
- * bodies as everywhere (bc.cuh).  Work items: one per copied cell / per column, region by region. */
-struct CFillRegion {                                               /* one ghost region of my box, as a block of work items */
-  int first;                                                        /* index of its first item in the flattened item space */
-  int ext0, ext1, lo0, lo1, lo2;                                    /* item -> cell: (t % ext0 + lo0, (t / ext0) % ext1 + lo1, t / (ext0 ext1) + lo2) */
-  int ndom, d0, d1, d2;                                             /* domain-normal axes (0: plain copy) and their inward strides */
-  int src_rank, shift;                                              /* block whose box the values come from (-1: mine), offset into its frame */
-};
-struct CFillPlan { int nitems, nregions; CFillRegion reg[26]; };
-/* built once per launch by one thread: shape 0 = NO_CORNERS (faces + edges), 1 = BOX (+ corners) */
-template <int N>
-__device__ static void c_fill_cluster_plan(CFillPlan *plan, const int box_shape, const int *bx, const int *rank_of)
-{
-  typedef Geo<N> G;
-  const int st[3] = { 1, G::jS, G::kS };
-  int n = 0, items = 0;
-  for (int reg = 0; reg < 27; reg++) {
-    const int r[3] = { reg % 3 - 1, (reg / 3) % 3 - 1, reg / 9 - 1 };
-    const int nz = (r[0] != 0) + (r[1] != 0) + (r[2] != 0);
-    if (nz == 0 || (nz == 3 && !box_shape)) continue;
-    int nb[3] = { bx[0], bx[1], bx[2] }, ndom = 0, d[3] = { 0, 0, 0 }, shift = 0;
-    bool seam[3] = { false, false, false };
-    for (int a = 0; a < 3; a++) {
-      if (r[a] == 0) continue;
-      const bool is_seam = (r[a] > 0) == (bx[a] == 0);               /* the neighbour is on my high side iff I am the low box */
-      if (is_seam) { seam[a] = true; nb[a] = 1 - bx[a]; shift -= r[a] * N * st[a]; }
-      else d[ndom++] = r[a] < 0 ? st[a] : -st[a];                    /* inward stride of a domain-normal axis, ascending axis order */
-    }
-    int ext[3], lo[3];
-    for (int a = 0; a < 3; a++) {
-      if (r[a] == 0) { ext[a] = N; lo[a] = 0; }
-      else if (seam[a]) { ext[a] = 2; lo[a] = r[a] < 0 ? -2 : N; }
-      else { ext[a] = 1; lo[a] = r[a] < 0 ? -1 : N; }                /* domain-normal axis: the column's nearest ghost cell */
-    }
-    CFillRegion &R = plan->reg[n++];
-    R.first = items;  R.ext0 = ext[0];  R.ext1 = ext[1];  R.lo0 = lo[0];  R.lo1 = lo[1];  R.lo2 = lo[2];
-    R.ndom = ndom;  R.d0 = d[0];  R.d1 = d[1];  R.d2 = d[2];
-    R.src_rank = (nb[0] != bx[0] || nb[1] != bx[1] || nb[2] != bx[2]) ? rank_of[nb[0] + 2 * nb[1] + 4 * nb[2]] : -1;
-    R.shift = shift;
-    items += ext[0] * ext[1] * ext[2];
-  }
-  plan->nitems = items;  plan->nregions = n;
-}
-/* Ghost fill of THIS block's box of the clustered level.  `v` points at cell (0,0,0) of the vector in this block's shared memory;
- * every block keeps the vector at the same shared-memory address, so the same cell of a neighbouring box is
- * map_shared_rank(pointer, its rank).  bx[a] in {0,1}: the box's position; along axis a the side facing the other box is a SEAM
- * (ghost cells = the neighbour's interior cells, exchange_boundary), the other side the DOMAIN boundary (boundary condition).  A
- * ghost region whose outside axes are all seams is copied; otherwise it is a set of BC columns along the domain axes, read --
- * where the region also crosses a seam -- from the neighbour across that seam (the image device_level.cu resolves into
- * FillBC::src).  Same column bodies as everywhere (bc.cuh).  One work item per copied cell / per column, all regions in ONE item
- * space so that every thread's remote loads are in flight at once (region after region cost a round trip each: 12 us per fill). */
-template <int N>
-__device__ static void c_fill_cluster(double *v, const CFillPlan *plan, const bool force_v2)
-{
-  typedef Geo<N> G;
-  cg::cluster_group cluster = cg::this_cluster();
-  const bool v2 = force_v2 || N < 4;
-  const int nitems = plan->nitems, nreg = plan->nregions;
-  for (int t = threadIdx.x; t < nitems; t += blockDim.x) {
-    int q = 0;
-    while (q + 1 < nreg && plan->reg[q + 1].first <= t) q++;
-    const CFillRegion R = plan->reg[q];
-    const int u = t - R.first;
-    const int off = (u % R.ext0 + R.lo0) + ((u / R.ext0) % R.ext1 + R.lo1) * G::jS + (u / (R.ext0 * R.ext1) + R.lo2) * G::kS;
-    const double *src = (R.src_rank >= 0 ? cluster.map_shared_rank(v, R.src_rank) + R.shift : v) + off;
-    if (R.ndom == 0) v[off] = src[0];
-    else if (v2) bc_v2_col_zero_rest(src, v + off, R.ndom, R.d0, R.d1, R.d2);
-    else if (R.ndom == 1) bc_v4_col1(src, v + off, R.d0, R.d0);
-    else if (R.ndom == 2) bc_v4_col2(src, v + off, R.d0, R.d1, R.d0, R.d1);
-    else bc_v4_col3(src, v + off, R.d0, R.d1, R.d2, R.d0, R.d1, R.d2);
-  }
-}
-
-/* restriction (restriction.c:54-57) of this block's box of the clustered level into its octant of the single coarse box, which
- * lives in block 0's shared memory: `coarse` is already mapped to block 0 and points at cell (0,0,0) of the coarse vector */
-template <int N>
-__device__ static void c_restrict_cluster(double *coarse, const int cjS, const int ckS, const double *fine, const int *bx)
-{
-  typedef Geo<N> G;
-  constexpr int H = N / 2;
-  for (int c = threadIdx.x; c < H * H * H; c += blockDim.x) {
-    const int i = c % H, j = (c / H) % H, k = c / (H * H);
-    const double *r = fine + 2 * i + 2 * j * G::jS + 2 * k * G::kS;
-    coarse[(bx[0] * H + i) + (bx[1] * H + j) * cjS + (bx[2] * H + k) * ckS] =
-        (r[0] + r[1] + r[G::jS] + r[1 + G::jS] + r[G::kS] + r[1 + G::kS] + r[G::jS + G::kS] + r[1 + G::jS + G::kS]) * 0.125;
-  }
-}
-/* interpolation_v2 / _v4 from the coarse box in block 0's shared memory (ghost cells filled by the phase before) into this block's box */
-template <int N, int W>
-__device__ static void c_interp_cluster(double *fine, const double prescale, const double *coarse, const int cjS, const int ckS, const int *bx)
-{
-  typedef Geo<N> G;
-  constexpr int H = N / 2;
-  for (int c = threadIdx.x; c < H * H * H; c += blockDim.x) {
-    const int i = c % H, j = (c / H) % H, k = c / (H * H);
-    c_interp_cell<W>(coarse + (bx[0] * H + i) + (bx[1] * H + j) * cjS + (bx[2] * H + k) * ckS, cjS, ckS, fine + 2 * i + 2 * j * G::jS + 2 * k * G::kS, G::jS, G::kS, prescale);
   }
 }
 
@@ -481,20 +357,18 @@ __device__ __forceinline__ void bulk_store(double *gmem_dst, const double *smem_
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"((unsigned)__cvta_generic_to_shared(smem_src)), "r"(bytes) : "memory");
 }
 
-/* CL: the kernel runs as ONE cluster of 8 thread blocks; level 0 of the chain is the clustered level (CoarseLevel::clustered),
- * one box per block; every other level lives in block 0, which alone runs their phases. */
-template <bool CL>
-__device__ __forceinline__ void coarse_cycle_body(const CoarseArgs &Ain, double *dyn, unsigned long long *s_bar_p, int *s_geo, CFillPlan *s_plan)
+__global__ void __launch_bounds__(COARSE_THREADS, 1) coarse_cycle_kernel(const __grid_constant__ CoarseArgs Ain)
 {
+  extern __shared__ __align__(128) double dyn[];
+  __shared__ __align__(8) unsigned long long s_bar;
   CoarseArgs &A = *reinterpret_cast<CoarseArgs *>(dyn);
   constexpr int ARGS_DOUBLES = (int)((sizeof(CoarseArgs) + 127) / 128) * 16;
   double *prod = dyn + ARGS_DOUBLES;
   double *red = prod + BOTTOM_MAX_CELLS + 1;
   double *pool = red + 34 + ((16 - (BOTTOM_MAX_CELLS + 1 + 34) % 16) % 16);        /* a multiple of 128 bytes from dyn: bulk copies need 16 */
-  const unsigned bar = (unsigned)__cvta_generic_to_shared(s_bar_p);
-  const int rank = CL ? (int)cg::this_cluster().block_rank() : 0;
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar);
   if (threadIdx.x == 0) {
-    s_prof_on = Ain.profile && rank == 0;
+    s_prof_on = Ain.profile;
     for (int c = 0; c < CP_N; c++) s_prof[c] = 0;
     s_prof[CP_N] = clock64();  s_prof[CP_TOTAL] = -s_prof[CP_N];
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
@@ -507,32 +381,20 @@ __device__ __forceinline__ void coarse_cycle_body(const CoarseArgs &Ain, double 
   }
   __syncthreads();
   PDL_WAIT();
-  int *bx = s_geo, *rank_of = s_geo + 3;                           /* clustered level: my box's position, block of every position */
-  if (CL && threadIdx.x == 0) {
-    const CoarseLevel &G = Ain.lv[0];
-    for (int b = 0; b < 8; b++) {
-      const int c0 = G.low[3 * b] / G.L.dim, c1 = G.low[3 * b + 1] / G.L.dim, c2 = G.low[3 * b + 2] / G.L.dim;
-      rank_of[c0 + 2 * c1 + 4 * c2] = b;
-      if (b == rank) { bx[0] = c0; bx[1] = c1; bx[2] = c2; }
-    }
-    c_fill_cluster_plan<8>(&s_plan[0], 0, bx, rank_of);
-    c_fill_cluster_plan<8>(&s_plan[1], 1, bx, rank_of);
-  }
   if (threadIdx.x == 0) {                                          /* request the resident vectors: one bulk copy each */
     unsigned total = 0;
     for (int l = 0; l < Ain.nlevels; l++) {
       const CoarseLevel &G = Ain.lv[l];
-      if (G.smem_offset < 0 || (rank != 0 && !G.clustered)) continue;
+      if (G.smem_offset < 0) continue;
       A.lv[l].L.base = pool + G.smem_offset;
       for (int sl = 0; sl < G.nslots; sl++) if (G.slot_io[sl] & 1) total += (unsigned)G.L.volume * 8u;
     }
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
     for (int l = 0; l < Ain.nlevels; l++) {
       const CoarseLevel &G = Ain.lv[l];
-      if (G.smem_offset < 0 || (rank != 0 && !G.clustered)) continue;
-      const size_t box0 = G.clustered ? (size_t)rank * G.gnvec : 0;                /* my box of the clustered level */
+      if (G.smem_offset < 0) continue;
       for (int sl = 0; sl < G.nslots; sl++)
-        if (G.slot_io[sl] & 1) bulk_load(pool + G.smem_offset + (size_t)sl * G.L.volume, G.gbase + (box0 + G.slot_id[sl]) * G.L.volume, (unsigned)G.L.volume * 8u, bar);
+        if (G.slot_io[sl] & 1) bulk_load(pool + G.smem_offset + (size_t)sl * G.L.volume, G.gbase + (size_t)G.slot_id[sl] * G.L.volume, (unsigned)G.L.volume * 8u, bar);
     }
   }
   asm volatile(
@@ -545,57 +407,13 @@ __device__ __forceinline__ void coarse_cycle_body(const CoarseArgs &Ain, double 
       "COARSE_DONE:\n"
       "}\n" ::"r"(bar) : "memory");
   __syncthreads();
-  if (CL) cg::this_cluster().sync();                               /* every block's box is in place before anybody reads a neighbour's */
   CPROF(CP_LOAD);
 
-  bool alone = false;                                              /* the last phase ran in block 0 only */
 #pragma unroll 1
   for (int ph = 0; ph < A.nphases; ph++) {
     const Phase P = A.prog[ph];
     const CoarseLevel &V = A.lv[P.lv];
     double *fb = pool + V.smem_offset;                              /* shared-memory address space stays visible to the compiler on the fast paths */
-    if (CL && V.clustered) {
-      /* ---- a phase of the clustered level: every block on its own box ---- */
-      typedef Geo<8> G8;
-      if (alone) { cg::this_cluster().sync(); alone = false; }      /* block 0 is back from the coarser levels */
-      double *cell0 = fb + G8::ORG;
-      switch (P.op) {
-        case PH_FILL:
-          c_fill_cluster<8>(cell0 + P.a * G8::VOL, &s_plan[P.b != 0 ? 1 : 0], P.c != 0);
-          __syncthreads();                                          /* the sweep that follows reads this block's memory only */
-          CPROF(CP_FILL);
-          break;
-        case PH_STENCIL: {
-          const double *gv = V.gbase + (size_t)rank * V.gnvec * G8::VOL + G8::ORG;     /* the operator data of my box, in global memory */
-          c_stencil_fast_ptr<8>(cell0 + P.b * G8::VOL, cell0 + P.c * G8::VOL, cell0 + P.d * G8::VOL, gv + (size_t)VECTOR_DINV * G8::VOL, gv + (size_t)VECTOR_BETA_I * G8::VOL,
-                                gv + (size_t)VECTOR_BETA_J * G8::VOL, gv + (size_t)VECTOR_BETA_K * G8::VOL, V.h2inv, V.c1[P.e], V.c2[P.e], P.a, P.e, A.b);
-          cg::this_cluster().sync();                                /* the next fill reads the neighbours' boxes */
-          CPROF(CP_STENCIL);
-          break;
-        }
-        case PH_RESTRICT_ZERO: {
-          const CoarseLevel &Vc = A.lv[1];
-          double *coarse = cg::this_cluster().map_shared_rank(pool + Vc.smem_offset + (size_t)P.a * Vc.L.volume + Vc.L.origin, 0);
-          c_restrict_cluster<8>(coarse, Vc.L.jStride, Vc.L.kStride, cell0 + P.b * G8::VOL, bx);
-          if (rank == 0) c_zero(Vc.L, P.c);
-          cg::this_cluster().sync();
-          CPROF(CP_RESTRICT);
-          break;
-        }
-        default: {                                                  /* PH_INTERP3 / PH_INTERP5 into the clustered level */
-          const CoarseLevel &Vc = A.lv[1];
-          const double *coarse = cg::this_cluster().map_shared_rank(pool + Vc.smem_offset + (size_t)P.b * Vc.L.volume + Vc.L.origin, 0);
-          if (P.op == PH_INTERP3) c_interp_cluster<8, 3>(cell0 + P.a * G8::VOL, 1.0, coarse, Vc.L.jStride, Vc.L.kStride, bx);
-          else                    c_interp_cluster<8, 5>(cell0 + P.a * G8::VOL, 0.0, coarse, Vc.L.jStride, Vc.L.kStride, bx);
-          cg::this_cluster().sync();
-          CPROF(CP_INTERP);
-          break;
-        }
-      }
-      continue;
-    }
-    alone = true;
-    if (CL && rank != 0) continue;                                  /* the coarser levels live in block 0 */
     switch (P.op) {
       case PH_FILL:
         if (V.fast == 8)      c_fill_fast<8>(fb + Geo<8>::ORG + P.a * Geo<8>::VOL, P.b != 0, P.c != 0);
@@ -648,34 +466,16 @@ __device__ __forceinline__ void coarse_cycle_body(const CoarseArgs &Ain, double 
   if (threadIdx.x == 0) {
     for (int l = 0; l < Ain.nlevels; l++) {
       const CoarseLevel &G = Ain.lv[l];
-      if (G.smem_offset < 0 || (rank != 0 && !G.clustered)) continue;
-      const size_t box0 = G.clustered ? (size_t)rank * G.gnvec : 0;
+      if (G.smem_offset < 0) continue;
       for (int sl = 0; sl < G.nslots; sl++)
-        if (G.slot_io[sl] & 2) bulk_store(G.gbase + (box0 + G.slot_id[sl]) * G.L.volume, pool + G.smem_offset + (size_t)sl * G.L.volume, (unsigned)G.L.volume * 8u);
+        if (G.slot_io[sl] & 2) bulk_store(G.gbase + (size_t)G.slot_id[sl] * G.L.volume, pool + G.smem_offset + (size_t)sl * G.L.volume, (unsigned)G.L.volume * 8u);
     }
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
   __syncthreads();
-  if (CL) cg::this_cluster().sync();                               /* nobody leaves while a neighbour may still read its shared memory */
   CPROF(CP_STORE);
   if (s_prof_on && threadIdx.x == 0) { s_prof[CP_TOTAL] += clock64(); for (int c = 0; c < CP_N; c++) g_coarse_prof[c] = s_prof[c]; }
-}
-
-__global__ void __launch_bounds__(COARSE_THREADS, 1) coarse_cycle_kernel(const __grid_constant__ CoarseArgs Ain)
-{
-  extern __shared__ __align__(128) double dyn[];
-  __shared__ __align__(8) unsigned long long s_bar;
-  __shared__ int s_geo[12];
-  coarse_cycle_body<false>(Ain, dyn, &s_bar, s_geo, nullptr);
-}
-__global__ void __launch_bounds__(COARSE_THREADS, 1) coarse_cluster_kernel(const __grid_constant__ CoarseArgs Ain)
-{
-  extern __shared__ __align__(128) double dyn[];
-  __shared__ __align__(8) unsigned long long s_bar;
-  __shared__ int s_geo[12];
-  __shared__ CFillPlan s_plan[2];
-  coarse_cycle_body<true>(Ain, dyn, &s_bar, s_geo, s_plan);
 }
 
 /* ---- host side ------------------------------------------------------------------------------------ */
@@ -713,25 +513,6 @@ static int level_is_coarse_eligible(const level_type *level, int is_top, int is_
   return 1;
 }
 
-/* 2^3 boxes of 8^3 cells, all mine, Dirichlet: the level can be the CLUSTERED top of a chain (one box per thread block of an
- * 8-block cluster, coarse.cu header) */
-static int g_coarse_cluster = 0;
-static int level_is_cluster_eligible(const level_type *level)
-{
-  if (!g_coarse_cluster) return 0;
-  if (level->boxes_in.i != 2 || level->boxes_in.j != 2 || level->boxes_in.k != 2 || level->num_my_boxes != 8 || level->box_dim != 8) return 0;
-  if (level->boundary_condition.type != BC_DIRICHLET || level->must_subtract_mean == 1) return 0;
-  if (level->box_ghosts != 2 || level->box_jStride != Geo<8>::jS || level->box_kStride != Geo<8>::kS || level->box_volume != Geo<8>::VOL) return 0;
-  for (int s = 0; s < STENCIL_MAX_SHAPES; s++)
-    if (level->exchange_ghosts[s].num_sends || level->exchange_ghosts[s].num_recvs) return 0;
-  if (level->restriction[RESTRICT_CELL].num_sends || level->interpolation.num_recvs) return 0;      /* the level below is mine too */
-  for (int b = 0; b < 8; b++) {
-    const box_type *B = &level->my_boxes[b];
-    if ((B->low.i % 8) || (B->low.j % 8) || (B->low.k % 8) || B->low.i > 8 || B->low.j > 8 || B->low.k > 8) return 0;
-  }
-  return 1;
-}
-
 /* Can levels `from`..bottom of this hierarchy run in the single-block kernel?  (all of them small,
  * entirely local to this rank, Dirichlet, and a single-box bottom the BiCGStab body can solve) */
 extern "C" int hpgmg_coarse_chain_eligible(mg_type *MG, int from)
@@ -743,8 +524,6 @@ extern "C" int hpgmg_coarse_chain_eligible(mg_type *MG, int from)
     if (m && atol(m) > 0) g_coarse_max_cells = atol(m) > COARSE_MAX_CELLS ? COARSE_MAX_CELLS : atol(m);
     const char *f = getenv("HPGMG_B200_COARSE_FAST");               /* 0: generic bodies on every level (A/B parity check) */
     if (f) g_coarse_fast = atoi(f);
-    const char *c = getenv("HPGMG_B200_COARSE_CLUSTER");            /* 0: the 2^3 x 8^3 level through the fused box kernels, one launch per operator */
-    if (c) g_coarse_cluster = atoi(c);
   }
   if (!g_coarse_enabled) return 0;
 #ifdef VECTOR_ALPHA
@@ -753,13 +532,7 @@ extern "C" int hpgmg_coarse_chain_eligible(mg_type *MG, int from)
   const int bottom = MG->num_levels - 1;
   if (from > bottom || bottom - from + 1 > COARSE_MAX_LEVELS) return 0;
   if (coarse_program_length(bottom - from + 1, 1) > COARSE_MAX_PHASES) return 0;
-  for (int l = from; l <= bottom; l++) {
-    if (level_is_coarse_eligible(MG->levels[l], l == from, l == bottom)) continue;
-    /* the top of the chain may be the clustered level, if the level below it is a resident single box of 8^3 */
-    if (l == from && l < bottom && g_coarse_smem && g_coarse_fast && level_is_cluster_eligible(MG->levels[l]) && MG->levels[l + 1]->box_dim == 8 &&
-        MG->levels[l + 1]->num_my_boxes == 1 && MG->levels[l + 1]->boxes_in.i == 1) continue;
-    return 0;
-  }
+  for (int l = from; l <= bottom; l++) if (!level_is_coarse_eligible(MG->levels[l], l == from, l == bottom)) return 0;
   const level_type *B = MG->levels[bottom];
   if (B->num_my_boxes != 1 || B->boxes_in.i != 1 || B->box_dim > BOTTOM_MAX_DIM || B->box_dim < 2) return 0;
   if (B->numVectors < VECTORS_RESERVED + 8) return 0;
@@ -852,20 +625,6 @@ extern "C" void hpgmg_coarse_cycle(mg_type *MG, int from, int mode_ftail, int ze
     int ids[COARSE_MAX_SLOTS], io[COARSE_MAX_SLOTS], n = 0;
     auto add = [&](int id, int flags) { for (int q = 0; q < n; q++) if (ids[q] == id) { io[q] |= flags; return q; } ids[n] = id; io[n] = flags; return n++; };
     const int s_temp = add(VECTOR_TEMP, 3), s_e = add(e_id, 3), s_R = add(R_id, 3);
-    V.gnvec = level->numVectors;
-    if (l == from && l < bottom && !level_is_coarse_eligible(level, 1, 0) && !stop && (used + (size_t)n * V.L.volume + 16) * sizeof(double) + 4096 <= budget) {      /* 4 KB: the cluster kernel's fill plans (static) */
-      /* the clustered top level: TEMP, e, R of one box per thread block; eligibility was checked by hpgmg_coarse_chain_eligible.
-       * (If the resident levels below left no room, the level falls through to the generic global-memory bodies of block 0.) */
-      V.clustered = 1;
-      V.smem_offset = (int)used;
-      used += ((size_t)n * V.L.volume + 15) / 16 * 16;
-      V.nslots = n;  V.L.nvec = n;
-      for (int q = 0; q < n; q++) { V.slot_id[q] = (unsigned char)ids[q]; V.slot_io[q] = (unsigned char)io[q]; }
-      V.s_dinv = VECTOR_DINV;  V.s_bi = VECTOR_BETA_I;  V.s_bj = VECTOR_BETA_J;  V.s_bk = VECTOR_BETA_K;      /* read from the global slab */
-      S[l - from].temp = s_temp;  S[l - from].e = s_e;  S[l - from].R = s_R;
-      V.fast = 8;
-      continue;
-    }
     const int s_dinv = add(VECTOR_DINV, 1), s_bi = add(VECTOR_BETA_I, 1), s_bj = add(VECTOR_BETA_J, 1), s_bk = add(VECTOR_BETA_K, 1);
     int kry[8] = { 0 };
     if (l == bottom) for (int q = 0; q < 8; q++) kry[q] = add(VECTORS_RESERVED + q, 0);     /* scratch of the solver: every one is written before it is read */
@@ -915,14 +674,5 @@ extern "C" void hpgmg_coarse_cycle(mg_type *MG, int from, int mode_ftail, int ze
     configured = true;
   }
   if (hpgmg_ablate(4)) return;
-  if (A.lv[0].clustered) {
-    static bool configured_cl = false;
-    if (!configured_cl) {
-      CUDA_CHECK(cudaFuncSetAttribute(coarse_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, COARSE_SMEM_MAX - 4096));
-      configured_cl = true;
-    }
-    hpgmg_launch_cluster("coarse_cluster_kernel", coarse_cluster_kernel, dim3(8), dim3(COARSE_THREADS), smem, A);
-    return;
-  }
   LAUNCH(coarse_cycle_kernel, 1, COARSE_THREADS, smem, A);
 }
