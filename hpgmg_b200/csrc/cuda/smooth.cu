@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) stencil_generic_kernel(const StencilArgs 
 #include <vector>
 
 /* switches kept for A/B parity checks (tests/test_gpu_parity.py::test_kernel_variants_give_the_same_bits); read once */
-static int g_force_generic = -1, g_tma = 1, g_tma_blocks = 0, g_zigzag = 1, g_diag = 1, g_pair_kernel = 1, g_tma_minplanes = 8, g_box_fused_max = 16;
+static int g_force_generic = -1, g_tma = 1, g_tma_blocks = 0, g_zigzag = 1, g_diag = 1, g_pair_kernel = 1, g_tma_minplanes = 4, g_box_fused_max = 16;
 
 static void stencil_env(void)
 {
@@ -179,7 +179,7 @@ static void launch_tma(const StencilArgs &A)
    * tiles that are neighbours in j then fetch their common halo rows at the same time and the second
    * fetch hits L2 (measured on `7 8`: 256 blocks = one column each 189 us; 296 blocks with an even but
    * unaligned split of the plane space 234 us).  Chunks only while the grid still fits the resident
-   * slots (MINB blocks per SM) and keeps >= 8 planes per block. */
+   * slots (MINB blocks per SM) and keeps >= 4 planes per block (measured on `7 8`: 16 planes 5.97 ms, 8 planes 5.78, 4 planes 5.74). */
   const long long slots = (long long)MINB * hpgmg_rt_sm_count(), columns = total / n;
   long long chunks = slots / columns;
   if (chunks > n / g_tma_minplanes) chunks = n / g_tma_minplanes;

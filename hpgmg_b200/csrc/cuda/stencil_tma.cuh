@@ -10,12 +10,14 @@
  *    of x, beta_i, beta_j, beta_k PF steps ahead into ring buffers; completion is counted by mbarriers
  *    (complete_tx::bytes).  No LDGSTS / address arithmetic in the compute warps (the cp.async version
  *    spent 16 LDGSTS = 128 LSU cycles per warp and plane on it).
- *  - layout: rows are stored as they are in memory (TMA cannot split parities).  Bank conflicts of the
- *    stride-2 red-black accesses are avoided by the lane mapping instead: even lanes work on row r, odd
- *    lanes on row r+1 of a row pair; the active cells of the two rows have opposite i-parity, so the 16
- *    lanes of a half-warp touch 16 distinct 8-byte banks.
- *  - addressing: a lane keeps ONE 32-bit shared address per ring slot (its active cell); every stencil
- *    operand is a load at a compile-time offset from it (LDS [R+imm]).
+ *  - layout: rows are stored as they are in memory (TMA cannot split parities).  GSRB: bank conflicts of the stride-2
+ *    red-black accesses are avoided by the lane mapping: a thread owns an i-pair (one active cell per sweep), even lanes work
+ *    on row r, odd lanes on row r+1 of a row pair; the active cells of the two rows have opposite i-parity, so the 16 lanes of
+ *    a half-warp touch 16 distinct 8-byte banks.  Residual / Chebyshev / apply_op: a thread owns the j-pair (i,j), (i,j+1);
+ *    lanes are consecutive cells of a row (conflict-free), and the two stencils share their common operands (pure loads
+ *    merged by the compiler: 85 LDS per cell pair instead of 110).
+ *  - addressing: a lane keeps ONE 32-bit shared address per ring slot; every stencil operand is a load at a compile-time
+ *    offset from it (LDS [R+imm]).
  *  - scheduling: block b owns the planes [P*b/G, P*(b+1)/G) of the linearised (box, tile, k) space and
  *    walks them as segments of one column each.  The launcher (smooth.cu: launch_tma) picks G = columns x
  *    equal k-chunks, so that every block is exactly one chunk and all blocks march k in step; any other G
