@@ -133,6 +133,13 @@ struct FillTable {
   FillCopy *copies;  int ncopies;
   FillBC   *bc;      int nbc;         /* local-source columns */
   FillBC   *late;    int nlate;       /* columns that need data from another GPU first */
+  /* the same copies and local-source columns regrouped for the fill kernel: items that are neighbours in i and 16-byte
+   * aligned on both sides are ONE item moving two doubles (copies2, bc2: columns i and i+1 of a face / edge whose normal
+   * has no i component); the rest stay single (copies1, bc1).  Half the items, 16-byte accesses. */
+  FillCopy *copies2; int ncopies2;
+  FillCopy *copies1; int ncopies1;
+  FillBC   *bc2;     int nbc2;
+  FillBC   *bc1;     int nbc1;
 };
 
 /* The same ghost fill (NO_CORNERS shape) binned by the compute tile that needs each value: the fused box kernels

@@ -49,6 +49,10 @@ static void free_fill_tables(hpgmg_device_level *D)
     if (T.copies) CUDA_CHECK(cudaFree(T.copies));
     if (T.bc) CUDA_CHECK(cudaFree(T.bc));
     if (T.late) CUDA_CHECK(cudaFree(T.late));
+    if (T.copies2) CUDA_CHECK(cudaFree(T.copies2));
+    if (T.copies1) CUDA_CHECK(cudaFree(T.copies1));
+    if (T.bc2) CUDA_CHECK(cudaFree(T.bc2));
+    if (T.bc1) CUDA_CHECK(cudaFree(T.bc1));
     memset(&T, 0, sizeof(T));
   }
 }
@@ -195,6 +199,34 @@ static void build_fill_tables(level_type *level, hpgmg_device_level *D)
     if (s == STENCIL_SHAPE_NO_CORNERS && late.empty() && level->exchange_ghosts[s].num_sends == 0 && level->exchange_ghosts[s].num_recvs == 0)
       build_tile_table(level, D, copies, now);
     FillTable &T = D->fill[s];
+    {
+      /* pairs for the fill kernel (FillTable, common.cuh).  Offsets count doubles from a 16-byte aligned base and strides are
+       * even, so an even offset is a 16-byte aligned address. */
+      std::vector<FillCopy> c2, c1;
+      for (size_t e = 0; e < copies.size(); e++) {
+        if (e + 1 < copies.size() && (copies[e].src & 1) == 0 && (copies[e].dst & 1) == 0 && copies[e + 1].src == copies[e].src + 1 && copies[e + 1].dst == copies[e].dst + 1) {
+          c2.push_back(copies[e]);
+          e++;
+        } else c1.push_back(copies[e]);
+      }
+      std::vector<FillBC> b2, b1;
+      for (size_t e = 0; e < now.size(); e++) {
+        const bool i_tangential = (now[e].subtype % 3) == 1;                    /* the domain normal has no i component */
+        if (i_tangential && e + 1 < now.size() && (now[e].src & 1) == 0 && (now[e].dst & 1) == 0 && now[e + 1].subtype == now[e].subtype &&
+            now[e + 1].src == now[e].src + 1 && now[e + 1].dst == now[e].dst + 1) {
+          b2.push_back(now[e]);
+          e++;
+        } else b1.push_back(now[e]);
+      }
+      auto normals = [](const FillBC &it) { return ((it.subtype % 3) != 1) + (((it.subtype % 9) / 3) != 1) + ((it.subtype / 9) != 1); };
+      auto by_kind = [&](const FillBC &x, const FillBC &y) { return normals(x) < normals(y); };
+      std::stable_sort(b2.begin(), b2.end(), by_kind);
+      std::stable_sort(b1.begin(), b1.end(), by_kind);
+      T.copies2 = upload_items(c2);  T.ncopies2 = (int)c2.size();
+      T.copies1 = upload_items(c1);  T.ncopies1 = (int)c1.size();
+      T.bc2 = upload_items(b2);      T.nbc2 = (int)b2.size();
+      T.bc1 = upload_items(b1);      T.nbc1 = (int)b1.size();
+    }
     T.copies = upload_items(copies);  T.ncopies = (int)copies.size();
     T.bc = upload_items(now);         T.nbc = (int)now.size();
     T.late = upload_items(late);      T.nlate = (int)late.size();

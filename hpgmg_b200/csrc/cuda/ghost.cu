@@ -135,32 +135,93 @@ struct FillArgs {
   int id, version;
   const blockCopy_type *pack, *unpack;
   int npack, nfill_blocks, nunpack, nlate_blocks;
-  int ncopy_blocks;                              /* the first ncopy_blocks fill blocks copy FILL_BATCH x 256 ghost cells each */
+  /* fill blocks, in this order: pair copies, single copies (FILL_BATCH x 256 items each), pair columns, single columns (256 each) */
+  int nc2_blocks, nc1_blocks, nb2_blocks;
   P2PPlan *plan;
-  const FillCopy *copies;  int ncopies;
-  const FillBC *bc;        int nbc;
-  const FillBC *late;      int nlate;
+  const FillCopy *copies2;  int ncopies2;        /* two doubles per item (FillTable, common.cuh) */
+  const FillCopy *copies1;  int ncopies1;
+  const FillBC *bc2;        int nbc2;            /* columns i and i+1 */
+  const FillBC *bc1;        int nbc1;
+  const FillBC *late;       int nlate;
 };
+
+/* columns i and i+1 of a face (one normal axis) or edge (two) whose normal has no i component: the same extrapolation on
+ * the two halves of 16-byte operands (all strides are even, r and w 16-byte aligned) */
+__device__ __forceinline__ void bc_v4_col1_x2(const double *r, double *w, const int d0)
+{
+  const double2 x1 = *reinterpret_cast<const double2 *>(r + d0), x2 = *reinterpret_cast<const double2 *>(r + 2 * d0);
+  const double2 x3 = *reinterpret_cast<const double2 *>(r + 3 * d0), x4 = *reinterpret_cast<const double2 *>(r + 4 * d0);
+  double2 n, f;
+  quartic_pair(x1.x, x2.x, x3.x, x4.x, n.x, f.x);
+  quartic_pair(x1.y, x2.y, x3.y, x4.y, n.y, f.y);
+  *reinterpret_cast<double2 *>(w) = n;
+  *reinterpret_cast<double2 *>(w - d0) = f;
+}
+__device__ __forceinline__ void bc_v4_col2_x2(const double *r, double *w, const int d0, const int d1)
+{
+  double2 n[4], f[4];
+#pragma unroll
+  for (int J = 0; J < 4; J++) {
+    const double *o = r + (J + 1) * d1;
+    const double2 x1 = *reinterpret_cast<const double2 *>(o + d0), x2 = *reinterpret_cast<const double2 *>(o + 2 * d0);
+    const double2 x3 = *reinterpret_cast<const double2 *>(o + 3 * d0), x4 = *reinterpret_cast<const double2 *>(o + 4 * d0);
+    quartic_pair(x1.x, x2.x, x3.x, x4.x, n[J].x, f[J].x);
+    quartic_pair(x1.y, x2.y, x3.y, x4.y, n[J].y, f[J].y);
+  }
+  double2 nn, nf, fn, ff;
+  quartic_pair(n[0].x, n[1].x, n[2].x, n[3].x, nn.x, nf.x);
+  quartic_pair(n[0].y, n[1].y, n[2].y, n[3].y, nn.y, nf.y);
+  quartic_pair(f[0].x, f[1].x, f[2].x, f[3].x, fn.x, ff.x);
+  quartic_pair(f[0].y, f[1].y, f[2].y, f[3].y, fn.y, ff.y);
+  *reinterpret_cast<double2 *>(w) = nn;
+  *reinterpret_cast<double2 *>(w - d1) = nf;
+  *reinterpret_cast<double2 *>(w - d0) = fn;
+  *reinterpret_cast<double2 *>(w - d0 - d1) = ff;
+}
 
 /* fill block fb: copies in batches (records, then sources, then stores: FILL_BATCH independent loads in flight
  * per thread -- the copies are latency-, not bandwidth-bound), then one BC column per thread */
 #define FILL_BATCH 4
-__device__ __forceinline__ void fill_block(const FillArgs &A, const int fb)
+__device__ __forceinline__ void fill_block(const FillArgs &A, int fb)
 {
   const DLevel &L = A.L;
-  if (fb < A.ncopy_blocks) {
-    double *v = L.base + (size_t)A.id * (size_t)L.volume;
+  double *v = L.base + (size_t)A.id * (size_t)L.volume;
+  if (fb < A.nc2_blocks) {                                          /* ---- copies, two doubles per item ---- */
+    const int t0 = fb * (256 * FILL_BATCH) + threadIdx.x;
+    FillCopy c[FILL_BATCH];
+    double2 val[FILL_BATCH];
+#pragma unroll
+    for (int n = 0; n < FILL_BATCH; n++) { const int t = t0 + n * 256; c[n] = (t < A.ncopies2) ? A.copies2[t] : FillCopy{ -1, -1 }; }
+#pragma unroll
+    for (int n = 0; n < FILL_BATCH; n++) if (c[n].src >= 0) val[n] = *reinterpret_cast<const double2 *>(v + c[n].src);
+#pragma unroll
+    for (int n = 0; n < FILL_BATCH; n++) if (c[n].src >= 0) *reinterpret_cast<double2 *>(v + c[n].dst) = val[n];
+  } else if ((fb -= A.nc2_blocks) < A.nc1_blocks) {                 /* ---- copies, one double per item ---- */
     const int t0 = fb * (256 * FILL_BATCH) + threadIdx.x;
     FillCopy c[FILL_BATCH];
     double val[FILL_BATCH];
 #pragma unroll
-    for (int n = 0; n < FILL_BATCH; n++) { const int t = t0 + n * 256; c[n] = (t < A.ncopies) ? A.copies[t] : FillCopy{ -1, -1 }; }
+    for (int n = 0; n < FILL_BATCH; n++) { const int t = t0 + n * 256; c[n] = (t < A.ncopies1) ? A.copies1[t] : FillCopy{ -1, -1 }; }
 #pragma unroll
     for (int n = 0; n < FILL_BATCH; n++) if (c[n].src >= 0) val[n] = v[c[n].src];
 #pragma unroll
     for (int n = 0; n < FILL_BATCH; n++) if (c[n].src >= 0) v[c[n].dst] = val[n];
-  } else {
-    fill_items(L, A.id, A.ncopies + (fb - A.ncopy_blocks) * 256 + threadIdx.x, A.copies, A.ncopies, A.bc, A.nbc, A.version);
+  } else if ((fb -= A.nc1_blocks) < A.nb2_blocks) {                 /* ---- BC columns i, i+1 ---- */
+    const int t = fb * 256 + threadIdx.x;
+    if (t < A.nbc2) {
+      const FillBC it = A.bc2[t];
+      const BCNormal N = bc_normal(it.subtype, L.jStride, L.kStride);
+      if (A.version == 4) {
+        if (N.m == 1) bc_v4_col1_x2(v + it.src, v + it.dst, N.d[0]);
+        else          bc_v4_col2_x2(v + it.src, v + it.dst, N.d[0], N.d[1]);
+      } else {
+        bc_v2_col_zero_rest(v + it.src, v + it.dst, N.m, N.d[0], N.d[1], N.d[2]);
+        bc_v2_col_zero_rest(v + it.src + 1, v + it.dst + 1, N.m, N.d[0], N.d[1], N.d[2]);
+      }
+    }
+  } else {                                                           /* ---- single BC columns ---- */
+    fb -= A.nb2_blocks;
+    fill_items(L, A.id, fb * 256 + threadIdx.x, (const FillCopy *)nullptr, 0, A.bc1, A.nbc1, A.version);
   }
 }
 
@@ -248,12 +309,16 @@ void hpgmg_fill_ghosts(level_type *level, int id, int shape, int bc_version)
   FillArgs A;
   memset(&A, 0, sizeof(A));
   A.L = D->L;  A.id = id;  A.version = version;
-  A.copies = T.copies;  A.ncopies = T.ncopies;
-  A.bc = T.bc;          A.nbc = dirichlet ? T.nbc : 0;
-  if (level->box_dim >= 64 && hpgmg_ablate(256)) A.ncopies = 0;
-  if (level->box_dim >= 64 && hpgmg_ablate(512)) A.nbc = 0;
-  A.ncopy_blocks = (A.ncopies + 256 * FILL_BATCH - 1) / (256 * FILL_BATCH);
-  A.nfill_blocks = A.ncopy_blocks + (A.nbc + 255) / 256;
+  A.copies2 = T.copies2;  A.ncopies2 = T.ncopies2;
+  A.copies1 = T.copies1;  A.ncopies1 = T.ncopies1;
+  A.bc2 = T.bc2;          A.nbc2 = dirichlet ? T.nbc2 : 0;
+  A.bc1 = T.bc1;          A.nbc1 = dirichlet ? T.nbc1 : 0;
+  if (level->box_dim >= 64 && hpgmg_ablate(256)) A.ncopies2 = A.ncopies1 = 0;
+  if (level->box_dim >= 64 && hpgmg_ablate(512)) A.nbc2 = A.nbc1 = 0;
+  A.nc2_blocks = (A.ncopies2 + 256 * FILL_BATCH - 1) / (256 * FILL_BATCH);
+  A.nc1_blocks = (A.ncopies1 + 256 * FILL_BATCH - 1) / (256 * FILL_BATCH);
+  A.nb2_blocks = (A.nbc2 + 255) / 256;
+  A.nfill_blocks = A.nc2_blocks + A.nc1_blocks + A.nb2_blocks + (A.nbc1 + 255) / 256;
   if (remote) {
     A.pack = pack;  A.npack = npack;  A.unpack = unpack;  A.nunpack = nunpack;  A.plan = plan;
     A.late = T.late;  A.nlate = dirichlet ? T.nlate : 0;
