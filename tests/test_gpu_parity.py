@@ -549,9 +549,11 @@ def test_multi_gpu_fmg_equals_single_process_reference(gpu_lib, ranks):
         pytest.skip(f"needs {ranks} GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={ranks}", "--master-addr", "127.0.0.1",
-           "--master-port", str(29600 + ranks), os.path.join(root, "tools", "check_multigpu.py"), "5", "8"]
+           "--master-port", str(29600 + ranks), os.path.join(root, "tools", "check_multigpu.py"), "5", "8", "cells"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert "PARITY OK (bit-exact)" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    if ob.have_ref():                          # and u itself, every cell of every box on every rank
+        assert "cell by cell: u of every box on every rank equals" in r.stdout, r.stdout[-2000:]
 
 
 # ------------------------------------------------------------------------- the other solve drivers of mg.c
