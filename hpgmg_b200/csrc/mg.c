@@ -464,9 +464,11 @@ void MGBuild(mg_type *MG, level_type *fine, double a, double b, int minCoarseGri
 
 /* ------------------------------------------------------------------------------------------ */
 static void hpgmg_forget_norms(const mg_type *MG);
+static void hpgmg_pipe_drain(mg_type *MG);
 void MGDestroy(mg_type *MG)
 {
   const int chatty = (MG->my_rank == 0) && hpgmg_rt_verbose();
+  hpgmg_pipe_drain(MG);                                 /* solves submitted with hpgmg_fmg_solve_host_submit and never waited for */
   hpgmg_rt_sync();
   hpgmg_graph_drop_all(MG);
   hpgmg_forget_norms(MG);
@@ -813,6 +815,11 @@ int hpgmg_fmg_solve_host_submit(mg_type *MG, int onLevel, int u_id, int F_id, do
   hpgmg_rt_pipe_scalars(slot);
   count_vcycle_visits(MG, onLevel);
   return slot;
+}
+static void hpgmg_pipe_drain(mg_type *MG)
+{
+  for (int t = 0; t < 2; t++)
+    if (g_pipe[t].busy && g_pipe[t].MG == MG) { double s[3]; hpgmg_rt_pipe_wait(t, s); g_pipe[t].busy = 0; g_pipe[t].MG = NULL; }
 }
 double hpgmg_fmg_solve_host_wait(mg_type *MG, int ticket)
 {
