@@ -32,6 +32,18 @@ def test_library_exports_every_declared_symbol():
     assert not missing, f"declared in include/*.h but not exported: {missing}"
 
 
+def test_helmholtz_flavour_exports_the_same_surface():
+    """libhpgmg_b200_helmholtz.so = the same sources with -DUSE_HELMHOLTZ (the reference's compile-time switch, defines.h:12-26):
+    same exported functions; the vector-id map of that build is in include/hpgmg_defines.h under the same #if."""
+    helm = os.path.join(os.path.dirname(api.LIB_PATH), "libhpgmg_b200_helmholtz.so")
+    assert os.path.exists(helm), "build first: make -C hpgmg_b200/csrc"
+    lib = C.CDLL(helm)
+    missing = [n for n in sorted(declared_functions()) if not hasattr(lib, n)]
+    assert not missing, missing
+    text = open(os.path.join(ROOT, "include", "hpgmg_defines.h")).read()
+    assert "VECTOR_ALPHA     9" in text and "VECTOR_L1INV    10" in text and "VECTORS_RESERVED 11" in text      # reference defines.h:24-26
+
+
 def test_reference_link_surface_is_complete():
     """The 34 external symbols the reference's operators.fv4.o defines plus what mg.o/solvers.o/level.o
     export must all be provided, under the reference's names."""
