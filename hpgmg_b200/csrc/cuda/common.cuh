@@ -173,6 +173,8 @@ struct hpgmg_device_level {
                                                    then holds exactly 1/(A applied to the unit vector), which the GSRB kernel may
                                                    recompute instead of reading.  Cleared by every other writer of the vector
                                                    (hpgmg_note_vector_written: BLAS1, transfers, smoothers, uploads). */
+  int   *restrict_map;                          /* device [nboxes][4]: coarse box and coarse cell of cell (0,0,0) of every box (smooth.cu: residual fused with restriction) */
+  int    restrict_map_state;                    /* 0 not looked at yet, 1 available, -1 the level's restriction is not box-to-box on this GPU */
   double *tile_partials;                        /* scratch for dot/mean: one double per compute tile */
   blockCopy_type *tiles;                        /* device copy of level->my_blocks                  */
   int     ntiles;

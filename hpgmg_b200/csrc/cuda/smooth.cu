@@ -13,7 +13,8 @@
 #include "common.cuh"
 #include "stencil.cuh"
 
-enum { OP_APPLY = 0, OP_RESIDUAL = 1, OP_GSRB = 2, OP_CHEBY = 3, OP_REBUILD = 4 };
+enum { OP_APPLY = 0, OP_RESIDUAL = 1, OP_GSRB = 2, OP_CHEBY = 3, OP_REBUILD = 4,
+       OP_RESRES = 5 };   /* residual fused with the cell restriction that follows it in MGVCycle (k-marching kernel only) */
 
 /* The Helmholtz build (-DUSE_HELMHOLTZ, as in the reference: operators.fv4.c:56-85): A x = a*alpha*x - b*h2inv*(...).  The
  * reference subtracts (b*h2inv)*(...) from a*alpha*x; fv4_apply_op returns (-b*h2inv)*(...), the exact negation, and
@@ -39,6 +40,11 @@ struct StencilArgs {
                               stays clear of the boundary-condition ghost cells (the stored Dinv holds exactly that there) */
   int dom[3];              /* level dimensions in cells */
   double *norm_slot;       /* TMA residual kernel: also leave max |res| here (the norm the caller wants next), or NULL */
+  /* OP_RESRES: the residual is not stored; its restriction goes to vector rc_id of the coarse level Lc.  rmap[4 box] =
+   * { coarse box, coarse cell of the box's cell (0,0,0): i, j, k } */
+  DLevel Lc;
+  const int *rmap;
+  int rc_id;
 };
 
 /* generic one-thread-per-cell kernel (any box size) ------------------------------------------- */
@@ -162,6 +168,17 @@ static const TileMaps *tile_maps(const DLevel &L, const int w, const int xr, con
 
 static bool g_norm_fused = false;          /* did the last residual launch also produce the norm? */
 
+/* equal k-chunks per column of the marching kernel: as many as fit the resident slots, at least g_tma_minplanes planes each */
+static long long tma_chunks(const long long columns, const int n, const int minb)
+{
+  const long long slots = (long long)minb * hpgmg_rt_sm_count();
+  long long chunks = slots / columns;
+  if (chunks > n / g_tma_minplanes) chunks = n / g_tma_minplanes;
+  if (chunks < 1) chunks = 1;
+  while (n % chunks) chunks--;
+  return chunks;
+}
+
 template <int OP, int TI, int TJ, int PF, int MINB>
 static void launch_tma(const StencilArgs &A)
 {
@@ -180,11 +197,8 @@ static void launch_tma(const StencilArgs &A)
    * fetch hits L2 (measured on `7 8`: 256 blocks = one column each 189 us; 296 blocks with an even but
    * unaligned split of the plane space 234 us).  Chunks only while the grid still fits the resident
    * slots (MINB blocks per SM) and keeps >= 4 planes per block (measured on `7 8`: 16 planes 5.97 ms, 8 planes 5.78, 4 planes 5.74). */
-  const long long slots = (long long)MINB * hpgmg_rt_sm_count(), columns = total / n;
-  long long chunks = slots / columns;
-  if (chunks > n / g_tma_minplanes) chunks = n / g_tma_minplanes;
-  if (chunks < 1) chunks = 1;
-  while (n % chunks) chunks--;
+  const long long columns = total / n;
+  const long long chunks = tma_chunks(columns, n, MINB);
   long long blocks = g_tma_blocks > 0 ? g_tma_blocks : columns * chunks;
   if (OP == OP_RESIDUAL && A.norm_slot) g_norm_fused = true;
   if (A.reverse && OP == OP_GSRB) LAUNCH((stencil_tma_kernel<OP, TI, TJ, PF, MINB, (OP == OP_GSRB)>), dim3((unsigned)blocks), dim3(C::NT), C::SMEM, A, M->x, M->b, total);
@@ -347,6 +361,71 @@ extern "C" void residual(level_type *level, int res_id, int x_id, int rhs_id, do
   StencilArgs A = {};
   A.x_id = x_id;  A.rhs_id = rhs_id;  A.out_id = res_id;  A.a = a;  A.b = b;
   fill_and_stencil<OP_RESIDUAL>(level, A, 1);
+}
+
+/* residual() followed by restriction(level_c, rc_id <- level, res_id, RESTRICT_CELL), as MGVCycle runs them (mg.c:1150-1151).
+ * Where the level runs the k-marching kernel and every box restricts into a box on this GPU, the residual kernel sums the
+ * 2x2x2 children itself (restriction.c:54-57, same order) and writes the coarse cells: the residual is neither written nor
+ * re-read (16 of its 48 B/cell) and the restriction launch disappears.  res_id then keeps its old contents -- MGVCycle
+ * overwrites it in the post-smooth. */
+static int *restriction_map(level_type *level, level_type *level_c)
+{
+  hpgmg_device_level *D = HPGMG_DEV(level);
+  if (D->restrict_map_state != 0) return D->restrict_map_state > 0 ? D->restrict_map : NULL;
+  if (g_capturing) return NULL;                          /* built by MGBuild (hpgmg_restriction_map_prepare); never inside a recording */
+  D->restrict_map_state = -1;
+  const communicator_type *Cf = &level->restriction[RESTRICT_CELL], *Cc = &level_c->restriction[RESTRICT_CELL];
+  const int nb = level->num_my_boxes, half = level->box_dim / 2;
+  if (nb == 0 || Cf->num_sends || Cf->num_recvs || Cc->num_sends || Cc->num_recvs || (level->box_dim & 3)) return NULL;
+  std::vector<int> map((size_t)4 * nb, -1);
+  std::vector<long> covered((size_t)nb, 0);
+  for (int e = 0; e < Cf->num_blocks[1]; e++) {
+    const blockCopy_type &B = Cf->blocks[1][e];
+    if (B.read.box < 0 || B.read.box >= nb || B.write.box < 0 || (B.read.i & 1) || (B.read.j & 1) || (B.read.k & 1)) return NULL;
+    const int m[4] = { B.write.box, B.write.i - B.read.i / 2, B.write.j - B.read.j / 2, B.write.k - B.read.k / 2 };
+    int *M = &map[(size_t)4 * B.read.box];
+    if (M[0] < 0) { M[0] = m[0]; M[1] = m[1]; M[2] = m[2]; M[3] = m[3]; }
+    else if (M[0] != m[0] || M[1] != m[1] || M[2] != m[2] || M[3] != m[3]) return NULL;
+    covered[B.read.box] += (long)B.dim.i * B.dim.j * B.dim.k;
+  }
+  for (int b = 0; b < nb; b++) if (covered[b] != (long)half * half * half) return NULL;
+  CUDA_CHECK(cudaMalloc(&D->restrict_map, map.size() * sizeof(int)));
+  CUDA_CHECK(cudaMemcpyAsync(D->restrict_map, map.data(), map.size() * sizeof(int), cudaMemcpyHostToDevice, g_stream));
+  CUDA_CHECK(cudaStreamSynchronize(g_stream));
+  D->restrict_map_state = 1;
+  return D->restrict_map;
+}
+extern "C" void hpgmg_restriction_map_prepare(level_type *level, level_type *level_c)
+{
+  if (hpgmg_rt_layout_only() || !HPGMG_DEV(level) || !HPGMG_DEV(level_c)) return;
+  restriction_map(level, level_c);
+}
+extern "C" void hpgmg_residual_then_restriction(level_type *level_c, int rc_id, level_type *level, int res_id, int x_id, int rhs_id, double a, double b)
+{
+  static int fuse = -1;
+  if (fuse < 0) { const char *e = getenv("HPGMG_B200_FUSE_RESTRICT"); fuse = e ? atoi(e) : 1; }
+  stencil_env();
+  const int n = level->box_dim;
+  const int *rmap = NULL;
+#ifndef VECTOR_ALPHA
+  if (fuse && !hpgmg_rt_profile() && !g_force_generic && g_tma && n % 32 == 0 && level->num_my_boxes > 0 && level_c->num_my_boxes > 0 && !hpgmg_ablate(32))
+    rmap = restriction_map(level, level_c);
+  /* the fused kernel pairs planes 2m, 2m+1 inside a block: k-chunks must be even (and not split by HPGMG_B200_TMA_BLOCKS) */
+  if (rmap && (g_tma_blocks > 0 || ((n / tma_chunks((long long)level->num_my_boxes * (n / 32) * (n / 8), n, 4)) & 1))) rmap = NULL;
+#endif
+  if (!rmap) {
+    residual(level, res_id, x_id, rhs_id, a, b);
+    restriction(level_c, rc_id, level, res_id, RESTRICT_CELL);
+    return;
+  }
+  hpgmg_note_vector_written(level_c, rc_id);
+  fill_ghosts(level, x_id);
+  StencilArgs A = {};
+  A.x_id = x_id;  A.rhs_id = rhs_id;  A.out_id = res_id;  A.a = a;  A.b = b;
+  A.L = dl_of(level);  A.low = HPGMG_DEV(level)->low;  A.h2inv = 1.0 / (level->h * level->h);
+  A.dom[0] = level->dim.i;  A.dom[1] = level->dim.j;  A.dom[2] = level->dim.k;
+  A.Lc = dl_of(level_c);  A.rmap = rmap;  A.rc_id = rc_id;
+  launch_tma<OP_RESRES, 32, 8, 1, 4>(A);
 }
 
 /* residual() followed by norm() of the result (mg.c:1316-1322, 1259-1262), the max taken inside the residual kernel

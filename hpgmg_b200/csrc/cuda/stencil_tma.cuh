@@ -202,6 +202,12 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
     const double *g_dinv = (OP == OP_GSRB || OP == OP_CHEBY) ? L.vec(box, VECTOR_DINV) + cell : nullptr;
     const double *g_xm1 = (OP == OP_CHEBY) ? L.vec(box, A.xm1_id) + cell : nullptr;
     double *g_out = L.vec(box, A.out_id) + cell;
+    double *c_out = nullptr;                                         /* OP_RESRES: the coarse cell under (lane, j), plane 0 of the coarse box */
+    double racc = 0.0;
+    if (OP == OP_RESRES) {
+      const int *M = A.rmap + 4 * box;
+      c_out = A.Lc.vec(M[0], A.rc_id) + (M[1] + ((i0 + ci_lane) >> 1)) + (M[2] + (j >> 1)) * A.Lc.jStride + M[3] * A.Lc.kStride;
+    }
     /* which cell of the pair is updated on plane k0 of this sweep (gsrb.c:55,100); flips every plane.
      * For the uncoloured operators it only fixes the ORDER in which the lane evaluates its two cells
      * (odd lanes start with the odd cell, so that a half-warp still covers all banks). */
@@ -306,6 +312,7 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
           double v;
           if (OP == OP_APPLY) v = Ax;
           else if (OP == OP_RESIDUAL) { v = (c ? rhs2.y : rhs2.x) - Ax; const double f = fabs(v); if (f > vmax) vmax = f; }
+          else if (OP == OP_RESRES) v = (c ? rhs2.y : rhs2.x) - Ax;
           else {                                                     /* OP_CHEBY, chebyshev.c:90 */
             const double xn = PX(0, 0, 0);
             v = xn + A.c1 * (xn - (c ? xm2.y : xm2.x)) + A.c2 * (c ? dinv2.y : dinv2.x) * ((c ? rhs2.y : rhs2.x) - Ax);
@@ -314,7 +321,17 @@ stencil_tma_kernel(const StencilArgs A, const __grid_constant__ CUtensorMap map_
         }
         out2 = make_double2(res[0], res[1]);
       }
-      if (JP) { g_out[k * kS] = out2.x; g_out[k * kS + jS] = out2.y; }
+      if (OP == OP_RESRES) {
+        /* restriction.c:54-57: (f000 + f100 + f010 + f110 + f001 + f101 + f011 + f111) * 0.125, summed left to right.  This
+         * lane holds (i, j) and (i, j+1) of plane k, lane+1 the cells i+1; k-chunks start on even planes and j is even. */
+        const double o0 = __shfl_down_sync(0xffffffffu, out2.x, 1), o1 = __shfl_down_sync(0xffffffffu, out2.y, 1);
+        if ((k & 1) == 0) racc = ((out2.x + o0) + out2.y) + o1;
+        else {
+          racc = (((racc + out2.x) + o0) + out2.y) + o1;
+          if ((lane & 1) == 0) c_out[(k >> 1) * A.Lc.kStride] = racc * 0.125;
+        }
+      }
+      else if (JP) { g_out[k * kS] = out2.x; g_out[k * kS + jS] = out2.y; }
       else *reinterpret_cast<double2 *>(g_out + k * kS) = out2;
 
       sx = sx + 1 == C::XP ? 0 : sx + 1;

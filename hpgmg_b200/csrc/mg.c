@@ -427,6 +427,7 @@ void MGBuild(mg_type *MG, level_type *fine, double a, double b, int minCoarseGri
   build_restriction(MG, RESTRICT_FACE_K);
   build_interpolation(MG);
   for (int l = 0; l < MG->num_levels; l++) hpgmg_device_level_upload_transfer_lists(MG->levels[l]);
+  for (int l = 0; l + 1 < MG->num_levels; l++) hpgmg_restriction_map_prepare(MG->levels[l], MG->levels[l + 1]);   /* residual fused with restriction (smooth.cu) */
   /* collective: swap buffer / flag addresses of every inter-level message (comm.cu) */
   for (int l = 0; l + 1 < MG->num_levels; l++) {
     for (int t = 0; t < 4; t++) hpgmg_comm_register_transfer(&MG->levels[l]->restriction[t], &MG->levels[l + 1]->restriction[t]);
@@ -536,8 +537,7 @@ void MGVCycle(mg_type *MG, int e_id, int R_id, double a, double b, int level)
   }
   level_type *Lc = MG->levels[level + 1];
   smooth(L, e_id, R_id, a, b);
-  residual(L, VECTOR_TEMP, e_id, R_id, a, b);
-  restriction(Lc, R_id, L, VECTOR_TEMP, RESTRICT_CELL);
+  hpgmg_residual_then_restriction(Lc, R_id, L, VECTOR_TEMP, e_id, R_id, a, b);      /* residual(); restriction(): mg.c:1150-1151 */
   zero_vector(Lc, e_id);
   MGVCycle(MG, e_id, R_id, a, b, level + 1);
   interpolation_vcycle(L, e_id, 1.0, Lc, e_id);

@@ -67,6 +67,10 @@ void hpgmg_norm_async(level_type *level, int id_a, int slot);
 void hpgmg_copy_norm_async(level_type *level, int id_c, int id_a, int slot);          /* norm(a) and c = 1.0*a in one pass */
 void hpgmg_residual_norm_async(level_type *level, int res_id, int x_id, int rhs_id, double a, double b, int slot);  /* residual, then its norm */
 
+/* residual(level, res <- rhs - A x) followed by restriction(level_c, rc <- res, RESTRICT_CELL): one kernel where the level allows it (smooth.cu) */
+void hpgmg_restriction_map_prepare(level_type *level, level_type *level_c);          /* MGBuild: the per-box map the fused kernel needs */
+void hpgmg_residual_then_restriction(level_type *level_c, int rc_id, level_type *level, int res_id, int x_id, int rhs_id, double a, double b);
+
 /* on-device bottom solver; returns 0 if the level is not eligible (caller falls back to the
  * host-driven BiCGStab in solvers.c) */
 int  hpgmg_bicgstab_device(level_type *level, int x_id, int R_id, double a, double b, double rtol);

@@ -606,6 +606,7 @@ VARIANTS = [
     {"HPGMG_B200_COARSE_FAST": "0"},                              # coarse kernel: generic bodies instead of the size-specialised ones
     {"HPGMG_B200_BOX_FUSED_MAX": "0"},                            # small boxes: separate ghost-fill kernel + operator kernel
     {"HPGMG_B200_BOX_FUSED_MAX": "32"},                           # fill-fused box kernel also on 32^3 boxes (instead of the TMA kernel)
+    {"HPGMG_B200_FUSE_RESTRICT": "0"},                            # residual and restriction as two kernels in MGVCycle
     {"HPGMG_B200_FUSE_NORM": "0"},                                # norm as a separate kernel after residual / R=F
     {"HPGMG_B200_INTERP_MARCH": "0"},                             # tiled interpolation on every level
     {"HPGMG_B200_INTERP_MARCH": "64"},                            # k-marching interpolation down to 16^3 boxes
