@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(BOTTOM_THREADS) bicgstab_kernel(const BottomAr
 {
   PDL_WAIT();
   __shared__ double prod[BOTTOM_MAX_CELLS];
-  __shared__ double red[33];
+  __shared__ double red[36];
   bicgstab_solve(A, prod, red);
 }
 

@@ -41,6 +41,7 @@ struct BottomCtx {
   double *prod;                 /* shared: BOTTOM_MAX_CELLS products / scratch */
   double *red;                  /* shared: per-warp partials + broadcast slot  */
   int n, cells, jS, kS;
+  int flip;                     /* which pair of result slots (red[32..33] / red[34..35]) the next reduction uses */
   __device__ int cell_offset(int c) const { return (c % n) + ((c / n) % n) * jS + (c / (n * n)) * kS; }
 };
 
@@ -62,7 +63,6 @@ __device__ static void b_fill_ghosts(const BottomCtx &C, const int id)
 /* out = A in   (mode 0)   or   out = rhs - A in   (mode 1) */
 __device__ static void b_apply(const BottomCtx &C, const int out_id, const int in_id, const int rhs_id, const int mode)
 {
-  __syncthreads();
   b_fill_ghosts(C, in_id);
   const DLevel &L = C.A.L;
   const double *x = L.vec(0, in_id), *bi = L.vec(0, C.A.ids.beta_i), *bj = L.vec(0, C.A.ids.beta_j), *bk = L.vec(0, C.A.ids.beta_k);
@@ -76,26 +76,50 @@ __device__ static void b_apply(const BottomCtx &C, const int out_id, const int i
   __syncthreads();
 }
 
-/* c = sa*a + sb*b */
-__device__ static void b_add(const BottomCtx &C, const int c_id, const double sa, const int a_id, const double sb, const int b_id)
+/* Every helper ends with ONE block barrier after its last write (reductions: two, around the serial sum), so that the next
+ * helper may read anything; independent updates share a barrier.  Reduction results alternate between two shared slots, which
+ * makes a third barrier (result read before the slot is written again) unnecessary.  The arithmetic of every cell and the
+ * order of every sum are those of solvers/bicgstab.c + operators/misc.c. */
+
+/* c = sa*a + sb*b  and  e = sd*d + sf*f   (two independent updates) */
+__device__ static void b_add2(const BottomCtx &C, const int c_id, const double sa, const int a_id, const double sb, const int b_id,
+                              const int e_id, const double sd, const int d_id, const double sf, const int f_id)
 {
   const DLevel &L = C.A.L;
-  double *c = L.vec(0, c_id);
-  const double *a = L.vec(0, a_id), *b = L.vec(0, b_id);
+  double *c = L.vec(0, c_id), *e = L.vec(0, e_id);
+  const double *a = L.vec(0, a_id), *b = L.vec(0, b_id), *d = L.vec(0, d_id), *f = L.vec(0, f_id);
   for (int q = threadIdx.x; q < C.cells; q += blockDim.x) {
     const int ijk = C.cell_offset(q);
     c[ijk] = sa * a[ijk] + sb * b[ijk];
+    e[ijk] = sd * d[ijk] + sf * f[ijk];
   }
   __syncthreads();
 }
-__device__ static void b_scale(const BottomCtx &C, const int c_id, const double sa, const int a_id)
+/* c = sa*a + sb*b, then e = sd*d + sf*c  (the second reads the first's result in the same cell) */
+__device__ static void b_add_chain(const BottomCtx &C, const int c_id, const double sa, const int a_id, const double sb, const int b_id,
+                                   const int e_id, const double sd, const int d_id, const double sf)
 {
   const DLevel &L = C.A.L;
-  double *c = L.vec(0, c_id);
+  double *c = L.vec(0, c_id), *e = L.vec(0, e_id);
+  const double *a = L.vec(0, a_id), *b = L.vec(0, b_id), *d = L.vec(0, d_id);
+  for (int q = threadIdx.x; q < C.cells; q += blockDim.x) {
+    const int ijk = C.cell_offset(q);
+    const double v = sa * a[ijk] + sb * b[ijk];
+    c[ijk] = v;
+    e[ijk] = sd * d[ijk] + sf * v;
+  }
+  __syncthreads();
+}
+__device__ static void b_scale2(const BottomCtx &C, const int c_id, const int e_id, const double sa, const int a_id)
+{
+  const DLevel &L = C.A.L;
+  double *c = L.vec(0, c_id), *e = L.vec(0, e_id);
   const double *a = L.vec(0, a_id);
   for (int q = threadIdx.x; q < C.cells; q += blockDim.x) {
     const int ijk = C.cell_offset(q);
-    c[ijk] = sa * a[ijk];
+    const double v = sa * a[ijk];
+    c[ijk] = v;
+    e[ijk] = v;
   }
   __syncthreads();
 }
@@ -111,35 +135,38 @@ __device__ static void b_mul(const BottomCtx &C, const int c_id, const double s,
   __syncthreads();
 }
 
-__device__ static double b_dot(const BottomCtx &C, const int a_id, const int b_id)
+/* dot(a,b) [and dot(a,d) if d_id >= 0]: products staged in shared memory, each sum by ONE thread in linear cell order
+ * (k,j,i: the reference's order on one tile) */
+__device__ static double b_dot(BottomCtx &C, const int a_id, const int b_id, const int d_id = -1, double *second = nullptr)
 {
   const DLevel &L = C.A.L;
-  const double *a = L.vec(0, a_id), *b = L.vec(0, b_id);
+  const double *a = L.vec(0, a_id), *b = L.vec(0, b_id), *d = d_id >= 0 ? L.vec(0, d_id) : nullptr;
+  double *prod2 = C.prod + C.cells;                              /* callers pass d_id only when 2*cells fit (bicgstab_solve) */
   for (int q = threadIdx.x; q < C.cells; q += blockDim.x) {
     const int ijk = C.cell_offset(q);
     C.prod[q] = a[ijk] * b[ijk];
+    if (d) prod2[q] = a[ijk] * d[ijk];
   }
   __syncthreads();
+  const int slot = 32 + 2 * C.flip;
   if (threadIdx.x == 0) {
     double s = 0.0;
-    for (int q = 0; q < C.cells; q++) s += C.prod[q];      /* k,j,i order == linear cell order */
-    C.red[32] = s;
+    for (int q = 0; q < C.cells; q++) s += C.prod[q];
+    C.red[slot] = s;
+  } else if (d && threadIdx.x == 32) {
+    double s = 0.0;
+    for (int q = 0; q < C.cells; q++) s += prod2[q];
+    C.red[slot + 1] = s;
   }
   __syncthreads();
-  const double r = C.red[32];
-  __syncthreads();
-  return r;
+  C.flip ^= 1;
+  if (second) *second = C.red[slot + 1];
+  return C.red[slot];
 }
 
-__device__ static double b_norm(const BottomCtx &C, const int a_id)
+/* max |a| over the cells; m: this thread's partial maximum (callers that have just produced the values pass it) */
+__device__ static double b_max(BottomCtx &C, double m)
 {
-  const DLevel &L = C.A.L;
-  const double *a = L.vec(0, a_id);
-  double m = 0.0;
-  for (int q = threadIdx.x; q < C.cells; q += blockDim.x) {
-    const double f = fabs(a[C.cell_offset(q)]);
-    if (f > m) m = f;
-  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const double other = __shfl_down_sync(0xffffffffu, m, o);
@@ -147,32 +174,60 @@ __device__ static double b_norm(const BottomCtx &C, const int a_id)
   }
   if ((threadIdx.x & 31) == 0) C.red[threadIdx.x >> 5] = m;
   __syncthreads();
+  const int slot = 32 + 2 * C.flip;
   if (threadIdx.x == 0) {
     for (int w = 1; w < (int)(blockDim.x >> 5); w++) if (C.red[w] > m) m = C.red[w];
-    C.red[32] = m;
+    C.red[slot] = m;
   }
   __syncthreads();
-  const double r = C.red[32];
-  __syncthreads();
-  return r;
+  C.flip ^= 1;
+  return C.red[slot];
+}
+__device__ static double b_norm(BottomCtx &C, const int a_id)
+{
+  const double *a = C.A.L.vec(0, a_id);
+  double m = 0.0;
+  for (int q = threadIdx.x; q < C.cells; q += blockDim.x) {
+    const double f = fabs(a[C.cell_offset(q)]);
+    if (f > m) m = f;
+  }
+  return b_max(C, m);
+}
+/* c = sa*a + sb*b; e = sd*d + sf*f; returns max |e| */
+__device__ static double b_add2_norm(BottomCtx &C, const int c_id, const double sa, const int a_id, const double sb, const int b_id,
+                                     const int e_id, const double sd, const int d_id, const double sf, const int f_id)
+{
+  const DLevel &L = C.A.L;
+  double *c = L.vec(0, c_id), *e = L.vec(0, e_id);
+  const double *a = L.vec(0, a_id), *b = L.vec(0, b_id), *d = L.vec(0, d_id), *f = L.vec(0, f_id);
+  double m = 0.0;
+  for (int q = threadIdx.x; q < C.cells; q += blockDim.x) {
+    const int ijk = C.cell_offset(q);
+    c[ijk] = sa * a[ijk] + sb * b[ijk];
+    const double v = sd * d[ijk] + sf * f[ijk];
+    e[ijk] = v;
+    const double av = fabs(v);
+    if (av > m) m = av;
+  }
+  return b_max(C, m);                                            /* its barriers also publish c and e */
 }
 
 /* the whole solve, executed cooperatively by all threads of the calling thread block;
- * prod: BOTTOM_MAX_CELLS doubles of shared memory, red: 33 doubles of shared memory */
+ * prod: BOTTOM_MAX_CELLS doubles of shared memory, red: 36 doubles of shared memory */
 __device__ static void bicgstab_solve(const BottomArgs &A, double *prod, double *red)
 {
-  BottomCtx C = { A, prod, red, A.L.dim, A.L.dim * A.L.dim * A.L.dim, A.L.jStride, A.L.kStride };
+  BottomCtx C = { A, prod, red, A.L.dim, A.L.dim * A.L.dim * A.L.dim, A.L.jStride, A.L.kStride, 0 };
 
   const int r0 = A.ids.r0, r = A.ids.r, p = A.ids.p, q = A.ids.q, s = A.ids.s, t = A.ids.t, Ap = A.ids.Ap, As = A.ids.As;
   const int DINV = A.ids.dinv, TEMP = A.ids.temp;
   const int x_id = A.x_id;
   const int jMax = 200;
+  const bool two_dots = 2 * C.cells <= BOTTOM_MAX_CELLS;            /* room for a second product array */
   int j = 0;
   bool failed = false, converged = false;
 
   b_apply(C, r0, x_id, A.R_id, 1);                        /* r0 = R - A x */
-  b_scale(C, r, 1.0, r0);
-  b_scale(C, p, 1.0, r0);
+  b_scale2(C, r, p, 1.0, r0);                             /* r = r0; p = r0 */
   double r_dot_r0 = b_dot(C, r, r0);
   const double norm_of_r0 = b_norm(C, r);
   if (r_dot_r0 == 0.0) converged = true;
@@ -185,30 +240,27 @@ __device__ static void bicgstab_solve(const BottomArgs &A, double *prod, double 
     if (Ap_dot_r0 == 0.0) { failed = true; break; }
     const double alpha = r_dot_r0 / Ap_dot_r0;
     if (isinf(alpha)) { failed = true; break; }
-    b_add(C, x_id, 1.0, x_id, alpha, q);
-    b_add(C, s, 1.0, r, -alpha, Ap);
-    const double norm_of_s = b_norm(C, s);
+    const double norm_of_s = b_add2_norm(C, x_id, 1.0, x_id, alpha, q, s, 1.0, r, -alpha, Ap);      /* x += alpha q; s = r - alpha Ap */
     if (norm_of_s == 0.0) { converged = true; break; }
     if (norm_of_s < A.rtol * norm_of_r0) { converged = true; break; }
     b_mul(C, t, 1.0, DINV, s);                     /* t = D^-1 s */
     b_apply(C, As, t, 0, 0);                              /* As = A t   */
-    const double As_dot_As = b_dot(C, As, As);
-    const double As_dot_s = b_dot(C, As, s);
+    double As_dot_s;
+    double As_dot_As;
+    if (two_dots) As_dot_As = b_dot(C, As, As, s, &As_dot_s);
+    else { As_dot_As = b_dot(C, As, As); As_dot_s = b_dot(C, As, s); }
     if (As_dot_As == 0.0) { converged = true; break; }
     const double omega = As_dot_s / As_dot_As;
     if (omega == 0.0) { failed = true; break; }
     if (isinf(omega)) { failed = true; break; }
-    b_add(C, x_id, 1.0, x_id, omega, t);
-    b_add(C, r, 1.0, s, -omega, As);
-    const double norm_of_r = b_norm(C, r);
+    const double norm_of_r = b_add2_norm(C, x_id, 1.0, x_id, omega, t, r, 1.0, s, -omega, As);      /* x += omega t; r = s - omega As */
     if (norm_of_r == 0.0) { converged = true; break; }
     if (norm_of_r < A.rtol * norm_of_r0) { converged = true; break; }
     const double r_dot_r0_new = b_dot(C, r, r0);
     if (r_dot_r0_new == 0.0) { failed = true; break; }
     const double beta = (r_dot_r0_new / r_dot_r0) * (alpha / omega);
     if (isinf(beta)) { failed = true; break; }
-    b_add(C, TEMP, 1.0, p, -omega, Ap);
-    b_add(C, p, 1.0, r, beta, TEMP);
+    b_add_chain(C, TEMP, 1.0, p, -omega, Ap, p, 1.0, r, beta);      /* TEMP = p - omega Ap; p = r + beta TEMP */
     r_dot_r0 = r_dot_r0_new;
   }
   if (threadIdx.x == 0) atomicAdd(A.iters, (double)j);
