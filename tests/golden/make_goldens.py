@@ -56,6 +56,43 @@ def solve_record(log2, boxes, cheby):
     return rec
 
 
+# the driver's compile-time variants.  (log2, boxes, periodic, helmholtz)
+VARIANTS = [(4, 1, True, False), (4, 8, True, False), (5, 8, True, False), (4, 27, True, False),
+            (4, 8, False, True), (5, 8, False, True), (4, 8, True, True), (4, 27, False, True)]
+
+
+def variant_record(log2, boxes, periodic, helmholtz):
+    """hpgmg-fv built with -DUSE_PERIODIC_BC and/or -DUSE_HELMHOLTZ (hpgmg-fv.c:276-302): the three Richardson solves, on ONE
+    OpenMP thread (the reference's mean() and dot() sum tile partials in thread order)."""
+    import ctypes as C
+    lib = None
+    a, b, vectors = 0.0, 1.0, None
+    if helmholtz:
+        lib = api.bind(C.CDLL(os.path.join(ob.REF_DIR, "libhpgmg_ref_helmholtz.so")), {k: api.SIGNATURES[k] for k in ob._REF_SYMBOLS})
+        a, b, vectors = 1.0, 1.0, 11
+    with ob.ref_threads(1):
+        H = ob.RefHierarchy(log2, boxes, bc=api.BC_PERIODIC if periodic else api.BC_DIRICHLET, library=lib, a=a, b=b, vectors=vectors)
+        norms = []
+        for l in range(3):
+            if l > 0:
+                H.call("restriction", H.level(l), api.VECTOR_F, H.level(l - 1), api.VECTOR_F, api.RESTRICT_CELL)
+            with ob.quiet():
+                H.L.zero_vector(H.level(l), api.VECTOR_U)
+                H.L.FMGSolve(H.mg, l, api.VECTOR_U, api.VECTOR_F, a, b, 1e-10)
+                H.L.residual(H.level(l), api.VECTOR_TEMP, api.VECTOR_U, api.VECTOR_F, a, b)
+                norms.append(H.L.norm(H.level(l), api.VECTOR_TEMP))
+        L1, L2, L0 = H.level(1), H.level(2), H.level(0)
+        H.call("restriction", L1, api.VECTOR_TEMP, L0, api.VECTOR_U, api.RESTRICT_CELL)
+        H.call("restriction", L2, api.VECTOR_TEMP, L1, api.VECTOR_U, api.RESTRICT_CELL)
+        H.call("add_vectors", L1, api.VECTOR_TEMP, 1.0, api.VECTOR_U, -1.0, api.VECTOR_TEMP)
+        H.call("add_vectors", L2, api.VECTOR_TEMP, 1.0, api.VECTOR_U, -1.0, api.VECTOR_TEMP)
+        e2h, e4h = H.call("norm", L1, api.VECTOR_TEMP), H.call("norm", L2, api.VECTOR_TEMP)
+    import math
+    return {"norms": norms, "error": e2h, "order": math.log(e4h / e2h) / math.log(2),
+            "eigs": [H.level(l).contents.dominant_eigenvalue_of_DinvA for l in range(H.num_levels)],
+            "dims": [H.level(l).contents.dim.i for l in range(H.num_levels)], "a": a, "b": b}
+
+
 def decomposition_record(log2, boxes_per_rank, ranks):
     out = []
     for r in range(ranks):
@@ -85,6 +122,13 @@ def main():
             continue
         print("decomposition", key, flush=True, file=sys.stderr)
         G["decompositions"][key] = decomposition_record(log2, bpr, ranks)
+    G.setdefault("variants", {})
+    for log2, boxes, periodic, helmholtz in VARIANTS:
+        key = f"{log2} {boxes} {'periodic' if periodic else 'dirichlet'} {'helmholtz' if helmholtz else 'poisson'}"
+        if key in G["variants"]:
+            continue
+        print("variant", key, flush=True, file=sys.stderr)
+        G["variants"][key] = variant_record(log2, boxes, periodic, helmholtz)
     with open(os.path.join(HERE, "goldens.json"), "w") as f:
         json.dump(G, f, indent=0, separators=(",", ":"))
     print("wrote goldens.json", file=sys.stderr)

@@ -105,3 +105,22 @@ def test_helmholtz_operator_equals_reference(helm, helm_ref, op):
                 helm.IterativeSolver(lb, U, Rr, A_, B_, 1e-3); helm_ref.IterativeSolver(rb, U, Rr, A_, B_, 1e-3); checks = [(H.num_levels - 1, U)]
         for l, vid in checks:
             assert_equal(helm, H, R, l, vid, "Helmholtz " + op)
+
+
+@pytest.mark.parametrize("key", ["4 8 dirichlet helmholtz", "5 8 dirichlet helmholtz", "4 8 periodic helmholtz", "4 27 dirichlet helmholtz"])
+def test_helmholtz_goldens(helm, key):
+    """The driver's three Richardson solves against tests/golden/goldens.json["variants"] (recorded from the reference built
+    -DUSE_HELMHOLTZ, make_goldens.py: variant_record)."""
+    log2, boxes, bc, _ = key.split()
+    gold = ob.goldens()["variants"][key]
+    helm.hpgmg_b200_use_graphs(1)
+    with api.Hierarchy(int(log2), int(boxes), bc=api.BC_PERIODIC if bc == "periodic" else api.BC_DIRICHLET, library=helm, a=A_, b=B_, vectors=NVEC) as H:
+        assert [H.level(l).contents.dominant_eigenvalue_of_DinvA for l in range(H.num_levels)] == gold["eigs"]
+        norms = []
+        for l in range(3):
+            if l > 0:
+                helm.restriction(H.level(l), F, H.level(l - 1), F, api.RESTRICT_CELL)
+            norms.append(H.fmg_solve(l)[0])
+        helm.richardson_error(H.mg, 0, U)
+        assert norms == gold["norms"]
+        assert helm.hpgmg_last_richardson_error() == gold["error"] and helm.hpgmg_last_richardson_order() == gold["order"]

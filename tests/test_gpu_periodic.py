@@ -104,3 +104,17 @@ def test_periodic_operator_equals_reference(gpu_lib, cfg, op):
                 raise AssertionError(op)
         for l, vid, where in checks:
             assert_level_equal(H, R, l, vid, where, "periodic " + op)
+
+
+@pytest.mark.parametrize("cfg", ["4 1", "4 8", "5 8", "4 27"])
+def test_periodic_goldens(gpu_lib, cfg):
+    """The driver's three Richardson solves (hpgmg-fv.c:351-366) against tests/golden/goldens.json["variants"], recorded from the
+    reference built -DUSE_PERIODIC_BC semantics (make_goldens.py: variant_record) -- holds without oracle/_ref too."""
+    log2, boxes = map(int, cfg.split())
+    gold = ob.goldens()["variants"][f"{log2} {boxes} periodic poisson"]
+    with api.Hierarchy(log2, boxes, bc=api.BC_PERIODIC) as H:
+        assert [H.level(l).contents.dim.i for l in range(H.num_levels)] == gold["dims"]
+        assert [H.level(l).contents.dominant_eigenvalue_of_DinvA for l in range(H.num_levels)] == gold["eigs"]
+        err, order, norms = H.richardson()
+        assert [n[0] for n in norms] == gold["norms"]
+        assert err == gold["error"] and order == gold["order"]
